@@ -1,0 +1,231 @@
+"""CPU oracle for the GuidedFilter hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file restates, in numpy, the algorithm of the reference's guided filter so
+that the CUDA path can be checked against it.  It is never imported by the
+product package (`cudaimageprocessing_b200`); only `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+`bench.py` may use it, and there only as the checker.
+
+What each function follows in the reference (paths relative to /root/reference):
+
+* gray guide, BORDER_REFLECT101, fixed divisor (2r+1)^2
+    GuidedFilter/main.cpp:236-252  (the "mycv" cv::blur composition; same maths
+    at main.cpp:30-47) and the fused GPU path GuidedFilter/guided_filter_d.cu:
+    421-858 (`gCalcAB` + `gWeightByABm`, border rule `reflectBorder` :415-418).
+* gray / per-channel, BORDER_TRUNCATE (window clipped to the image, divided by
+  the true pixel count)
+    GuidedFilter/guided_filter.cpp:28-66 (`GuidedFilter::run`) with
+    guided_filter_d.cu:251-262 (`gIntegralToMean` clip + area) and the
+    point-wise formulas :306-323 (a), :349-362 (b), :382-395 (q).
+* BORDER_REFLECT is what `cv::ximgproc::guidedFilter` (main.cpp:234) uses; that
+  function lives in OpenCV-contrib (un-vendored, version unpinned:
+  GuidedFilter/CMakeLists.txt:8), so it is restated from He et al., "Guided
+  Image Filtering", TPAMI 2013, eqs. (5), (6), (8) / (19)-(21).
+* colour guide (3x3 covariance): absent from the reference's own code (SURVEY
+  fact 5); restated from He et al. eqs. (19)-(21).  PARITY UNPINNED for this
+  variant: no golden vector of the reference exercises it.
+
+Pinning: `tests/test_oracle_golden.py` checks `guided_filter_gray` (float32
+mode) against the reference's golden PNG `adobe_image_4_myres.png`
+(r=7, eps=0.3; GuidedFilter/main.cpp:295-304) through the committed fixtures in
+`tests/golden/`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BORDER_REFLECT101 = 0   # gfedcb|abcdefgh|gfedcba   (cv::BORDER_DEFAULT, reflectBorder)
+BORDER_TRUNCATE = 1     # window clipped to the image, divide by true count (gIntegralToMean)
+BORDER_REFLECT = 2      # fedcba|abcdefgh|hgfedcb   (cv::ximgproc::guidedFilter)
+
+_BORDER_NAMES = {BORDER_REFLECT101: "reflect101", BORDER_TRUNCATE: "truncate", BORDER_REFLECT: "reflect"}
+
+
+def border_index(idx, n: int, mode: int) -> np.ndarray:
+    """Map (possibly out-of-range) coordinates to source coordinates.
+
+    REFLECT101 follows `reflectBorder` (guided_filter_d.cu:415-418) for a single
+    overshoot and extends it periodically (period 2n-2) the way OpenCV's
+    borderInterpolate does, so it stays defined when r >= n.  TRUNCATE returns -1
+    for coordinates outside the image (they contribute nothing).
+    """
+    idx = np.asarray(idx, dtype=np.int64)
+    if mode == BORDER_TRUNCATE:
+        return np.where((idx >= 0) & (idx < n), idx, -1)
+    if n == 1:
+        return np.zeros_like(idx)
+    if mode == BORDER_REFLECT101:
+        period = 2 * n - 2
+        m = np.mod(idx, period)
+        return np.where(m < n, m, period - m)
+    if mode == BORDER_REFLECT:
+        period = 2 * n
+        m = np.mod(idx, period)
+        return np.where(m < n, m, period - 1 - m)
+    raise ValueError(f"unknown border mode {mode}")
+
+
+def _window_sum_axis(a: np.ndarray, r: int, mode: int, axis: int) -> np.ndarray:
+    """Sum over [i-r, i+r] along `axis` with the border rule, float64 accumulate."""
+    n = a.shape[axis]
+    ext = border_index(np.arange(-r, n + r), n, mode)
+    a = np.moveaxis(a, axis, 0)
+    if mode == BORDER_TRUNCATE:
+        pad = np.zeros((r,) + a.shape[1:], dtype=a.dtype)
+        e = np.concatenate([pad, a, pad], axis=0)
+    else:
+        e = a[ext]
+    c = np.cumsum(e, axis=0, dtype=np.float64)
+    c = np.concatenate([np.zeros((1,) + c.shape[1:], dtype=np.float64), c], axis=0)
+    s = c[2 * r + 1: 2 * r + 1 + n] - c[0:n]
+    return np.moveaxis(s, 0, axis)
+
+
+def window_count(n: int, r: int, mode: int) -> np.ndarray:
+    """Number of pixels the 1-D window [i-r, i+r] covers (true count for TRUNCATE)."""
+    if mode == BORDER_TRUNCATE:
+        i = np.arange(n)
+        return (np.minimum(n - 1, i + r) - np.maximum(0, i - r) + 1).astype(np.float64)
+    return np.full(n, 2 * r + 1, dtype=np.float64)
+
+
+def box_sum(img: np.ndarray, r: int, mode: int) -> np.ndarray:
+    """(2r+1)^2 window sums of an HxW or HxWxC array, float64."""
+    a = np.asarray(img, dtype=np.float64)
+    return _window_sum_axis(_window_sum_axis(a, r, mode, 1), r, mode, 0)
+
+
+def box_mean(img: np.ndarray, r: int, mode: int, dtype=np.float64) -> np.ndarray:
+    """Box mean.
+
+    REFLECT101 == cv::blur(img, Size(2r+1,2r+1)) (main.cpp:241-244): float32 data,
+    double running sums, one multiply by 1/(2r+1)^2, cast back.  TRUNCATE ==
+    hBoxFilter (guided_filter_d.cu:868-924) with exact sums instead of the
+    reference's float32 integral image.
+    """
+    img = np.asarray(img)
+    h, w = img.shape[:2]
+    s = box_sum(img, r, mode)
+    cnt = np.outer(window_count(h, r, mode), window_count(w, r, mode))
+    if s.ndim == 3:
+        cnt = cnt[:, :, None]
+    return (s * (1.0 / cnt)).astype(dtype)
+
+
+def guided_filter_gray(I, p, r: int, eps: float, mode: int = BORDER_REFLECT101,
+                       dtype=np.float64, return_ab: bool = False):
+    """q = mean(a)*I + mean(b) with a = cov(I,p)/(var(I)+eps), b = mean(p) - a*mean(I).
+
+    Follows GuidedFilter/main.cpp:236-252 statement by statement.  With
+    dtype=float32 every Mat is float32 as in the reference (the KAT mode); with
+    float64 it is the ground truth the CUDA path is held to (<= 1e-4).
+    I and p may be HxW, or HxWxC with equal C (channels filtered independently --
+    `channel1 == channel2` branches, guided_filter_d.cu:968-971), or I HxW with
+    p HxWxC (`CN1` branches, :972-975).
+    """
+    I = np.asarray(I).astype(dtype)
+    p = np.asarray(p).astype(dtype)
+    if I.ndim == 2 and p.ndim == 3:
+        I = I[:, :, None]
+    eps = dtype(eps)
+    pm = box_mean(p, r, mode, dtype)
+    im = box_mean(I, r, mode, dtype)
+    ipm = box_mean(p * I, r, mode, dtype)
+    iim = box_mean(I * I, r, mode, dtype)
+    a = (ipm - pm * im) / (iim - im * im + eps)
+    b = pm - a * im
+    am = box_mean(a, r, mode, dtype)
+    bm = box_mean(b, r, mode, dtype)
+    q = (am * I + bm).astype(dtype)
+    if return_ab:
+        return q, a.astype(dtype), b.astype(dtype)
+    return q
+
+
+def guided_filter_color(I, p, r: int, eps: float, mode: int = BORDER_REFLECT101,
+                        dtype=np.float64):
+    """Colour-guide guided filter (He et al. 2013, eqs. 19-21).  PARITY UNPINNED.
+
+    I: HxWx3 guide.  p: HxW or HxWxC.  a_k = (Sigma_k + eps*U)^-1 (mean(I p) -
+    mu_k mean(p)), b_k = mean(p) - a_k^T mu_k, q = mean(a)^T I + mean(b).
+    """
+    I = np.asarray(I).astype(dtype)
+    p = np.asarray(p).astype(dtype)
+    squeeze = p.ndim == 2
+    if squeeze:
+        p = p[:, :, None]
+    h, w, _ = I.shape
+    mu = box_mean(I, r, mode, dtype)                         # H W 3
+    pm = box_mean(p, r, mode, dtype)                         # H W C
+    # 6 unique second moments
+    idx = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+    sig = np.empty((h, w, 3, 3), dtype=dtype)
+    for (i, j) in idx:
+        m = box_mean(I[:, :, i] * I[:, :, j], r, mode, dtype) - mu[:, :, i] * mu[:, :, j]
+        sig[:, :, i, j] = m
+        sig[:, :, j, i] = m
+    sig = sig + dtype(eps) * np.eye(3, dtype=dtype)
+    out = np.empty_like(p)
+    inv = np.linalg.inv(sig.astype(np.float64)).astype(dtype)
+    for c in range(p.shape[2]):
+        pc = p[:, :, c]
+        cov = np.stack([box_mean(I[:, :, i] * pc, r, mode, dtype) - mu[:, :, i] * pm[:, :, c]
+                        for i in range(3)], axis=-1)         # H W 3
+        a = np.einsum("hwij,hwj->hwi", inv, cov).astype(dtype)
+        b = pm[:, :, c] - np.sum(a * mu, axis=-1)
+        am = box_mean(a, r, mode, dtype)
+        bm = box_mean(b, r, mode, dtype)
+        out[:, :, c] = np.sum(am * I, axis=-1) + bm
+    return out[:, :, 0] if squeeze else out
+
+
+def guided_filter_class_run(I, p, r: int, eps: float, dtype=np.float64):
+    """`GuidedFilter::run` (guided_filter.cpp:28-66): TRUNCATE border, channel
+    combinations (1,1), (3,3) per channel, (guide 1, src 3).  The reference's
+    `gCalcBCN1` bug (guided_filter_d.cu:371-372) is NOT reproduced."""
+    return guided_filter_gray(I, p, r, eps, BORDER_TRUNCATE, dtype)
+
+
+def to_u8(q) -> np.ndarray:
+    """Mat::convertTo(CV_8U, 255.0) (main.cpp:295-297): saturate_cast<uchar>(cvRound(q*255)).
+    OpenCV scales a CV_32F Mat in float32 (cvt32f8u: `src*a + b` with float a, b) and cvRound
+    is round-half-to-even, so a float32 input is multiplied in float32 here too -- the KAT
+    has thousands of pixels sitting on x.5 after the 5x bilinear upscale."""
+    q = np.asarray(q)
+    if q.dtype == np.float32:
+        v = q * np.float32(255.0)
+    else:
+        v = q.astype(np.float64) * 255.0
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def integral_u8(img_u8: np.ndarray, wrap32: bool = False) -> np.ndarray:
+    """Inclusive summed-area table of a uint8 image in int64 (exact).
+
+    Follows Integral/integral_d.cu:863-893 (`hIntegral`; output W x H, no zero
+    row/column -- Integral/main.cpp:124 compares against cv::integral's
+    interior).  wrap32=True reduces mod 2^32 like the reference's int32 output.
+    """
+    s = np.cumsum(np.cumsum(np.asarray(img_u8, dtype=np.int64), axis=0), axis=1)
+    if wrap32:
+        s = s.astype(np.uint32).astype(np.int32)
+    return s
+
+
+def box_sum_u8(img_u8: np.ndarray, r: int, mode: int) -> np.ndarray:
+    """Exact integer (int64) window sums of a uint8 image."""
+    a = np.asarray(img_u8, dtype=np.int64)
+
+    def axis_sum(a, axis):
+        n = a.shape[axis]
+        a = np.moveaxis(a, axis, 0)
+        if mode == BORDER_TRUNCATE:
+            pad = np.zeros((r,) + a.shape[1:], dtype=np.int64)
+            e = np.concatenate([pad, a, pad], axis=0)
+        else:
+            e = a[border_index(np.arange(-r, n + r), n, mode)]
+        c = np.cumsum(e, axis=0)
+        c = np.concatenate([np.zeros((1,) + c.shape[1:], dtype=np.int64), c], axis=0)
+        return np.moveaxis(c[2 * r + 1: 2 * r + 1 + n] - c[0:n], 0, axis)
+
+    return axis_sum(axis_sum(a, 1), 0)
