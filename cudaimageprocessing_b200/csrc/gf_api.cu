@@ -1,0 +1,458 @@
+// gf_api.cu -- implementation of the C ABI declared in include/gf_b200.h.
+//
+// Host logic only: argument checks, kernel-family choice, launch geometry.  Every compute entry
+// launches hand-written sm_100a kernels; there is no CPU path (a missing device surfaces as
+// GF_ERR_CUDA from the first launch).
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/gf_b200.h"
+#include "gf_generic.cuh"
+#include "gf_job.h"
+#include "gf_pointwise.cuh"
+#include "gf_rt.h"
+#ifdef GF_HAVE_FAST
+#include "gf_fast.cuh"
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+thread_local const char* g_kernel = "none";
+std::atomic<int64_t> g_launches{0};
+
+int fail(gf_status s, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return (int)s;
+}
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return div_up(a, b) * b; }
+
+int check_common(const Job& j)
+{
+    if (!j.guide.ptr || !j.src.ptr || !j.dst.ptr) return fail(GF_ERR_INVALID, "null image pointer");
+    if (j.width <= 0 || j.height <= 0 || j.out_rows <= 0 || j.count <= 0)
+        return fail(GF_ERR_INVALID, "non-positive size (w=%d h=%d rows=%d count=%d)", j.width, j.height, j.out_rows, j.count);
+    if (j.r < 0) return fail(GF_ERR_INVALID, "negative radius %d", j.r);
+    if (j.border < 0 || j.border > 2) return fail(GF_ERR_INVALID, "unknown border mode %d", j.border);
+    if (!(j.eps >= 0.f)) return fail(GF_ERR_INVALID, "eps must be >= 0");
+    if (j.guide.stride < (int64_t)j.width * j.guide.channels || j.src.stride < (int64_t)j.width * j.src.channels ||
+        j.dst.stride < (int64_t)j.width * j.dst.channels)
+        return fail(GF_ERR_INVALID, "row stride smaller than a row");
+    if ((j.A.ptr == nullptr) != (j.B.ptr == nullptr)) return fail(GF_ERR_INVALID, "A and B must both be given or both be NULL");
+    if (j.out_y0 < 0 || j.out_y0 + j.out_rows > j.height) return fail(GF_ERR_INVALID, "output rows outside the image");
+    // the rows the filter reads (after the border rule) must be inside the buffer
+    int lo = j.height, hi = -1;
+    for (int y = j.out_y0 - 2 * j.r; y < j.out_y0 + j.out_rows + 2 * j.r; ++y) {
+        const int s = gf_map(y, j.height, j.border);
+        if (s < 0) continue;
+        lo = s < lo ? s : lo;
+        hi = s > hi ? s : hi;
+    }
+    if (lo < j.buf_y0 || hi >= j.buf_y0 + j.buf_rows)
+        return fail(GF_ERR_INVALID, "input buffer holds rows [%d,%d) but rows [%d,%d] are needed (2r halo missing?)",
+                    j.buf_y0, j.buf_y0 + j.buf_rows, lo, hi);
+    return GF_OK;
+}
+
+// ---- generic kernel geometry -------------------------------------------------------------------
+struct GenericCfg {
+    int win, wc, hb, nstrips, nbands;
+    bool ring_smem;
+    size_t smem_bytes, ring_floats_per_cta;
+};
+
+// nq_pub: values published per thread for the horizontal sums; nq_ring: values in the row ring
+int plan_generic(const Job& j, int halo_cols, int halo_rows, int nq_pub, int nq_ring, GenericCfg* c)
+{
+    auto smem_floats = [&](int win, bool ring) {
+        size_t n = (size_t)nq_pub * (win + 32);
+        if (ring) n += (size_t)nq_ring * (2 * j.r + 1) * win;
+        return n;
+    };
+    // halo_cols = 4r for the fused filter, 2r for the box filter
+    int sms = 148, cc_major = 0, cc_minor = 0;
+    gf_rt_device_info(&sms, &cc_major, &cc_minor);
+    const int cands[5] = {round_up(j.width + halo_cols, 32), 128, 256, 512, 1024};
+    const size_t max_smem = gf_rt_max_smem();
+    int best = -1;
+    double best_score = -1;
+    bool best_ring = false;
+    for (int i = 0; i < 5; ++i) {
+        const int win = cands[i];
+        if (win > 1024 || win - halo_cols < 32) {
+            if (!(i == 0 && win <= 1024 && win - halo_cols >= j.width)) continue;
+        }
+        const int wc = win - halo_cols;
+        if (wc < 1) continue;
+        const bool ring_fits = smem_floats(win, true) * sizeof(float) <= max_smem;
+        const int used = wc < j.width ? wc : j.width;
+        double score = (double)used / win + (ring_fits ? 1.0 : 0.0) - 1e-4 * win / 1024.0;
+        if (score > best_score) { best_score = score; best = win; best_ring = ring_fits; }
+    }
+    if (best < 0)
+        return fail(GF_ERR_UNSUPPORTED, "radius %d too large for the streaming kernel (needs %d halo columns of at most 1024 threads)",
+                    j.r, halo_cols);
+    c->win = best;
+    c->wc = best - halo_cols;
+    c->ring_smem = best_ring;
+    c->nstrips = div_up(j.width, c->wc);
+    const int target = 4 * sms;
+    int nb = target / (c->nstrips * j.count);
+    if (nb < 1) nb = 1;
+    int hb = div_up(j.out_rows, nb);
+    const int hb_min = 2 * halo_rows > 16 ? 2 * halo_rows : 16;   // keep the warm-up rows <= 50% of a band
+    if (hb < hb_min) hb = hb_min;
+    if (hb > j.out_rows) hb = j.out_rows;
+    c->hb = hb;
+    c->nbands = div_up(j.out_rows, hb);
+    c->smem_bytes = smem_floats(c->win, c->ring_smem) * sizeof(float);
+    c->ring_floats_per_cta = c->ring_smem ? 0 : (size_t)nq_ring * (2 * j.r + 1) * c->win;
+    return GF_OK;
+}
+
+GfArgs mk_args(const Job& j)
+{
+    GfArgs a;
+    a.guide = mk(j.guide); a.src = mk(j.src); a.dst = mk(j.dst); a.A = mk(j.A); a.B = mk(j.B);
+    a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.out_y0 = j.out_y0; a.out_rows = j.out_rows;
+    a.r = j.r; a.border = j.border; a.eps = j.eps; a.wc = 0; a.hb = 0; a.ring = nullptr;
+    return a;
+}
+
+template <class M>
+int launch_generic(const Job& j)
+{
+    GenericCfg c;
+    int rc = plan_generic(j, 4 * j.r, 4 * j.r, M::NQ1 + M::NQ2, M::NQ2, &c);
+    if (rc) return rc;
+    GfArgs a = mk_args(j);
+    a.wc = c.wc; a.hb = c.hb;
+    void* ring = nullptr;
+    if (!c.ring_smem) {
+        const size_t n = c.ring_floats_per_cta * c.nstrips * c.nbands * j.count * sizeof(float);
+        if (const char* e = gf_rt_alloc_async(&ring, n, j.stream)) return fail(GF_ERR_NOMEM, "ring scratch (%zu bytes): %s", n, e);
+        a.ring = (float*)ring;
+    }
+    auto kfn = gf_generic_kernel<M>;
+    if (const char* e = gf_rt_set_smem(kfn, c.smem_bytes)) return fail(GF_ERR_CUDA, "smem attribute: %s", e);
+    dim3 grid(c.nstrips, c.nbands, j.count), block(c.win);
+    GF_LAUNCH(kfn, grid, block, c.smem_bytes, j.stream, a);
+    const char* e = gf_rt_launch_error();
+    if (ring) gf_rt_free_async(ring, j.stream);
+    if (e) return fail(GF_ERR_CUDA, "gf_generic_kernel launch: %s", e);
+    g_launches++;
+    g_kernel = M::NQ1 == 4 ? "generic_gray" : "generic_color";
+    return GF_OK;
+}
+
+bool overlaps(const Plane& a, const Plane& b, int rows, int count)
+{
+    if (!a.ptr || !b.ptr) return false;
+    const float* a1 = a.ptr + (count - 1) * a.frame_stride + (int64_t)rows * a.stride;
+    const float* b1 = b.ptr + (count - 1) * b.frame_stride + (int64_t)rows * b.stride;
+    return a.ptr < b1 && b.ptr < a1;
+}
+
+int run_job(const Job& j)
+{
+    int rc = check_common(j);
+    if (rc) return rc;
+    bool done = false;
+#ifdef GF_HAVE_FAST
+    {
+        const char* name = nullptr;
+        const char* e = gf_fast_try(j, &done, &name);
+        if (done) {
+            if (e) rc = fail(GF_ERR_CUDA, "%s launch: %s", name, e);
+            else { rc = GF_OK; g_launches++; g_kernel = name; }
+        }
+    }
+#endif
+    if (!done) rc = j.color ? launch_generic<GfColorModel>(j) : launch_generic<GfGrayModel>(j);
+    return rc;
+}
+
+// Runs n jobs that write (channels of) one destination buffer.  The streaming kernels read
+// halos that other CTAs may already have overwritten, so a destination that aliases an input
+// goes through a stream-ordered temporary (the reference can run in place only because every
+// stage round-trips its scratch planes).
+int run_jobs(Job* js, int n)
+{
+    const Job& j0 = js[0];
+    if (!j0.dst.ptr || !j0.guide.ptr || !j0.src.ptr) return fail(GF_ERR_INVALID, "null image pointer");
+    const bool alias = overlaps(j0.dst, j0.guide, j0.buf_rows, j0.count) || overlaps(j0.dst, j0.src, j0.buf_rows, j0.count);
+    void* tmp = nullptr;
+    const size_t row_bytes = (size_t)j0.width * j0.dst.channels * sizeof(float);
+    const Plane user_dst = j0.dst;
+    int rc = GF_OK;
+    if (alias) {
+        if (j0.width <= 0 || j0.out_rows <= 0 || j0.count <= 0) return fail(GF_ERR_INVALID, "non-positive size");
+        const size_t bytes = row_bytes * j0.out_rows * j0.count;
+        if (const char* e = gf_rt_alloc_async(&tmp, bytes, j0.stream)) return fail(GF_ERR_NOMEM, "in-place temporary: %s", e);
+        for (int i = 0; i < n; ++i) {
+            js[i].dst.ptr = (const float*)tmp;
+            js[i].dst.stride = (int64_t)j0.width * j0.dst.channels;
+            js[i].dst.frame_stride = js[i].dst.stride * j0.out_rows;
+        }
+    }
+    for (int i = 0; i < n && rc == GF_OK; ++i) rc = run_job(js[i]);
+    if (tmp) {
+        if (rc == GF_OK)
+            for (int f = 0; f < j0.count; ++f)
+                if (const char* e = gf_rt_copy2d_async(const_cast<float*>(user_dst.ptr) + f * user_dst.frame_stride,
+                                                       user_dst.stride * sizeof(float),
+                                                       (const float*)tmp + f * js[0].dst.frame_stride, row_bytes, row_bytes,
+                                                       j0.out_rows, j0.stream))
+                    rc = fail(GF_ERR_CUDA, "copy back: %s", e);
+        gf_rt_free_async(tmp, j0.stream);
+    }
+    return rc;
+}
+
+int64_t or_packed(int64_t stride, int width, int channels) { return stride > 0 ? stride : (int64_t)width * channels; }
+
+}  // namespace
+
+struct gf_filter {
+    int width, height, gch, sch;
+};
+
+extern "C" {
+
+const char* gf_last_error(void) { return g_err.c_str(); }
+int gf_version(void) { return 100; }
+const char* gf_last_kernel(void) { return g_kernel; }
+int64_t gf_launch_count(void) { return g_launches.load(); }
+
+int gf_device_info(int* sm_count, int* cc_major, int* cc_minor)
+{
+    int a = 0, b = 0, c = 0;
+    if (const char* e = gf_rt_device_info(&a, &b, &c)) return fail(GF_ERR_CUDA, "%s", e);
+    if (sm_count) *sm_count = a;
+    if (cc_major) *cc_major = b;
+    if (cc_minor) *cc_minor = c;
+    return GF_OK;
+}
+
+int gf_create(gf_handle* out, int width, int height, int guide_channels, int src_channels)
+{
+    if (!out) return fail(GF_ERR_INVALID, "null handle pointer");
+    *out = nullptr;
+    if (width <= 0 || height <= 0) return fail(GF_ERR_INVALID, "non-positive size %dx%d", width, height);
+    const bool ok = (guide_channels == 1 && (src_channels == 1 || src_channels == 3)) ||
+                    (guide_channels == 3 && (src_channels == 3 || src_channels == 1));
+    if (!ok) return fail(GF_ERR_UNSUPPORTED, "Do not support channel: %d, %d", guide_channels, src_channels);
+    gf_filter* f = new gf_filter{width, height, guide_channels, src_channels};
+    *out = f;
+    return GF_OK;
+}
+
+int gf_destroy(gf_handle h)
+{
+    delete h;
+    return GF_OK;
+}
+
+int gf_run(gf_handle h, const float* guide, const float* src, float* dst, int r, float eps, int border,
+           int64_t guide_stride, int64_t src_stride, int64_t dst_stride, void* stream)
+{
+    if (!h) return fail(GF_ERR_INVALID, "null handle");
+    Job j;
+    j.width = h->width; j.height = h->height; j.buf_rows = h->height; j.out_rows = h->height;
+    j.r = r; j.eps = eps; j.border = border; j.stream = stream;
+    const int64_t gs = or_packed(guide_stride, h->width, h->gch), ss = or_packed(src_stride, h->width, h->sch),
+                  ds = or_packed(dst_stride, h->width, h->sch);
+    if (h->gch == 3 && h->sch == 1) {           // colour guide, 3x3 covariance
+        j.color = true;
+        j.guide = Plane{guide, gs, 0, 3, 0};
+        j.src = Plane{src, ss, 0, 1, 0};
+        j.dst = Plane{dst, ds, 0, 1, 0};
+        j.A = j.B = Plane{nullptr, 0, 0, 1, 0};
+        return run_jobs(&j, 1);
+    }
+    // (1,1); (3,3) channel by channel; (1,3) one guide for three source channels
+    // (guided_filter_d.cu:968-975)
+    Job js[3];
+    for (int c = 0; c < h->sch; ++c) {
+        js[c] = j;
+        js[c].guide = Plane{guide, gs, 0, h->gch, h->gch == 1 ? 0 : c};
+        js[c].src = Plane{src, ss, 0, h->sch, c};
+        js[c].dst = Plane{dst, ds, 0, h->sch, c};
+        js[c].A = js[c].B = Plane{nullptr, 0, 0, 1, 0};
+    }
+    return run_jobs(js, h->sch);
+}
+
+int gf_guided_gray(const float* guide, const float* src, float* dst, float* A, float* B, int width, int height,
+                   int64_t guide_stride, int64_t src_stride, int64_t dst_stride, int64_t ab_stride, int r, float eps,
+                   int border, void* stream)
+{
+    Job j;
+    j.width = width; j.height = height; j.buf_rows = height; j.out_rows = height;
+    j.r = r; j.eps = eps; j.border = border; j.stream = stream;
+    j.guide = Plane{guide, or_packed(guide_stride, width, 1), 0, 1, 0};
+    j.src = Plane{src, or_packed(src_stride, width, 1), 0, 1, 0};
+    j.dst = Plane{dst, or_packed(dst_stride, width, 1), 0, 1, 0};
+    j.A = Plane{A, or_packed(ab_stride, width, 1), 0, 1, 0};
+    j.B = Plane{B, or_packed(ab_stride, width, 1), 0, 1, 0};
+    return run_jobs(&j, 1);
+}
+
+int gf_guided_color(const float* guide3, const float* src, float* dst, int width, int height, int src_channels,
+                    int64_t guide_stride, int64_t src_stride, int64_t dst_stride, int r, float eps, int border, void* stream)
+{
+    if (src_channels != 1 && src_channels != 3) return fail(GF_ERR_UNSUPPORTED, "Do not support channel: 3, %d", src_channels);
+    Job j;
+    j.width = width; j.height = height; j.buf_rows = height; j.out_rows = height;
+    j.r = r; j.eps = eps; j.border = border; j.stream = stream; j.color = true;
+    j.guide = Plane{guide3, or_packed(guide_stride, width, 3), 0, 3, 0};
+    j.A = j.B = Plane{nullptr, 0, 0, 1, 0};
+    Job js[3];
+    for (int c = 0; c < src_channels; ++c) {
+        js[c] = j;
+        js[c].src = Plane{src, or_packed(src_stride, width, src_channels), 0, src_channels, c};
+        js[c].dst = Plane{dst, or_packed(dst_stride, width, src_channels), 0, src_channels, c};
+    }
+    return run_jobs(js, src_channels);
+}
+
+int gf_guided_batch(const float* guide, const float* src, float* dst, int count, int width, int height, int guide_channels,
+                    int64_t guide_stride, int64_t src_stride, int64_t dst_stride, int64_t guide_frame_stride,
+                    int64_t src_frame_stride, int64_t dst_frame_stride, int r, float eps, int border, void* stream)
+{
+    if (guide_channels != 1 && guide_channels != 3) return fail(GF_ERR_UNSUPPORTED, "Do not support channel: %d, 1", guide_channels);
+    Job j;
+    j.count = count;
+    j.width = width; j.height = height; j.buf_rows = height; j.out_rows = height;
+    j.r = r; j.eps = eps; j.border = border; j.stream = stream; j.color = guide_channels == 3;
+    const int64_t gs = or_packed(guide_stride, width, guide_channels), ss = or_packed(src_stride, width, 1),
+                  ds = or_packed(dst_stride, width, 1);
+    j.guide = Plane{guide, gs, guide_frame_stride > 0 ? guide_frame_stride : gs * height, guide_channels, 0};
+    j.src = Plane{src, ss, src_frame_stride > 0 ? src_frame_stride : ss * height, 1, 0};
+    j.dst = Plane{dst, ds, dst_frame_stride > 0 ? dst_frame_stride : ds * height, 1, 0};
+    j.A = j.B = Plane{nullptr, 0, 0, 1, 0};
+    return run_jobs(&j, 1);
+}
+
+int gf_guided_gray_strip(const float* guide, const float* src, float* dst, int width, int global_height, int buf_y0,
+                         int buf_rows, int out_y0, int out_rows, int64_t guide_stride, int64_t src_stride,
+                         int64_t dst_stride, int r, float eps, int border, void* stream)
+{
+    Job j;
+    j.width = width; j.height = global_height; j.buf_y0 = buf_y0; j.buf_rows = buf_rows; j.out_y0 = out_y0; j.out_rows = out_rows;
+    j.r = r; j.eps = eps; j.border = border; j.stream = stream;
+    if (buf_rows <= 0 || buf_y0 < 0 || buf_y0 + buf_rows > global_height) return fail(GF_ERR_INVALID, "buffer rows outside the image");
+    j.guide = Plane{guide, or_packed(guide_stride, width, 1), 0, 1, 0};
+    j.src = Plane{src, or_packed(src_stride, width, 1), 0, 1, 0};
+    j.dst = Plane{dst, or_packed(dst_stride, width, 1), 0, 1, 0};
+    j.A = j.B = Plane{nullptr, 0, 0, 1, 0};
+    return run_jobs(&j, 1);
+}
+
+int gf_box_filter(const float* src, float* dst, int width, int height, int channels, int64_t src_stride, int64_t dst_stride,
+                  int r, int border, void* stream)
+{
+    if (channels < 1 || channels > 4) return fail(GF_ERR_UNSUPPORTED, "gScanLongRow Do not support channel: %d", channels);
+    Job j;
+    j.width = width; j.height = height; j.buf_rows = height; j.out_rows = height;
+    j.r = r; j.border = border; j.stream = stream;
+    j.src = Plane{src, or_packed(src_stride, width, channels), 0, channels, 0};
+    j.guide = j.src;
+    j.dst = Plane{dst, or_packed(dst_stride, width, channels), 0, channels, 0};
+    j.A = j.B = Plane{nullptr, 0, 0, 1, 0};
+    // reuse the halo check with r/2 semantics: the box filter needs r rows, not 2r -- the full
+    // image is always in the buffer here, so check_common cannot fail on coverage
+    int rc = check_common(j);
+    if (rc) return rc;
+    void* tmp = nullptr;
+    Job jj = j;
+    const size_t row_bytes = (size_t)width * channels * sizeof(float);
+    if (overlaps(j.dst, j.src, height, 1)) {   // in place, as guided_filter.cpp:59-60 does
+        if (const char* e = gf_rt_alloc_async(&tmp, row_bytes * height, stream)) return fail(GF_ERR_NOMEM, "in-place temporary: %s", e);
+        jj.dst.ptr = (const float*)tmp;
+        jj.dst.stride = (int64_t)width * channels;
+    }
+    GenericCfg c;
+    rc = plan_generic(jj, 2 * r, 2 * r, channels, 0, &c);
+    if (rc) { if (tmp) gf_rt_free_async(tmp, stream); return rc; }
+    GfArgs a = mk_args(jj);
+    a.wc = c.wc; a.hb = c.hb;
+    const size_t smem = c.smem_bytes;
+    dim3 grid(c.nstrips, c.nbands, 1), block(c.win);
+    switch (channels) {
+    case 1: { auto k = gf_box_kernel<1>; GF_LAUNCH(k, grid, block, smem, stream, a); break; }
+    case 2: { auto k = gf_box_kernel<2>; GF_LAUNCH(k, grid, block, smem, stream, a); break; }
+    case 3: { auto k = gf_box_kernel<3>; GF_LAUNCH(k, grid, block, smem, stream, a); break; }
+    default: { auto k = gf_box_kernel<4>; GF_LAUNCH(k, grid, block, smem, stream, a); break; }
+    }
+    const char* e = gf_rt_launch_error();
+    if (!e && tmp) e = gf_rt_copy2d_async(dst, j.dst.stride * sizeof(float), tmp, row_bytes, row_bytes, height, stream);
+    if (tmp) gf_rt_free_async(tmp, stream);
+    if (e) return fail(GF_ERR_CUDA, "gf_box_kernel: %s", e);
+    g_launches++;
+    g_kernel = "box";
+    return GF_OK;
+}
+
+static int pointwise(int op, const float* i0, const float* i1, const float* i2, const float* i3, float* out, int width,
+                     int height, int cs, int cg, int64_t ss, int64_t sg, float eps, void* stream, const char* name)
+{
+    if (!i0 || !i1 || !out || (op != GF_PW_MUL && !i2) || (op == GF_PW_CALC_A && !i3)) return fail(GF_ERR_INVALID, "%s: null pointer", name);
+    if (width <= 0 || height <= 0) return fail(GF_ERR_INVALID, "%s: non-positive size", name);
+    if (cs < 1 || !(cg == cs || cg == 1)) return fail(GF_ERR_UNSUPPORTED, "%s Do not support channel: %d, %d", name, cs, cg);
+    GfPwArgs a;
+    a.in0 = i0; a.in1 = i1; a.in2 = i2; a.in3 = i3; a.out = out;
+    a.width = width; a.height = height; a.cs = cs; a.cg = cg;
+    a.ss = or_packed(ss, width, cs); a.sg = or_packed(sg, width, cg); a.eps = eps;
+    dim3 block(256), grid(div_up(width, 256), height < 1024 ? height : 1024);
+    switch (op) {
+    case GF_PW_MUL: { auto k = gf_pointwise_kernel<GF_PW_MUL>; GF_LAUNCH(k, grid, block, 0, stream, a); break; }
+    case GF_PW_CALC_A: { auto k = gf_pointwise_kernel<GF_PW_CALC_A>; GF_LAUNCH(k, grid, block, 0, stream, a); break; }
+    case GF_PW_CALC_B: { auto k = gf_pointwise_kernel<GF_PW_CALC_B>; GF_LAUNCH(k, grid, block, 0, stream, a); break; }
+    default: { auto k = gf_pointwise_kernel<GF_PW_LINEAR>; GF_LAUNCH(k, grid, block, 0, stream, a); break; }
+    }
+    if (const char* e = gf_rt_launch_error()) return fail(GF_ERR_CUDA, "%s: %s", name, e);
+    g_launches++;
+    g_kernel = "pointwise";
+    return GF_OK;
+}
+
+int gf_multiply(const float* a, const float* b, float* c, int width, int height, int channels_a, int channels_b,
+                int64_t stride_a, int64_t stride_b, void* stream)
+{
+    return pointwise(GF_PW_MUL, a, b, nullptr, nullptr, c, width, height, channels_a, channels_b, stride_a, stride_b, 0.f, stream, "gMultiply");
+}
+
+int gf_calc_a(float* a, const float* pm, const float* im, const float* ipm, const float* iim, int width, int height,
+              int channels_s, int channels_g, int64_t stride_s, int64_t stride_g, float eps, void* stream)
+{
+    return pointwise(GF_PW_CALC_A, pm, im, ipm, iim, a, width, height, channels_s, channels_g, stride_s, stride_g, eps, stream, "gCalcA");
+}
+
+int gf_calc_b(float* b, const float* a, const float* pm, const float* im, int width, int height, int channels_s,
+              int channels_g, int64_t stride_s, int64_t stride_g, void* stream)
+{
+    return pointwise(GF_PW_CALC_B, a, im, pm, nullptr, b, width, height, channels_s, channels_g, stride_s, stride_g, 0.f, stream, "gCalcB");
+}
+
+int gf_linear_transform(const float* src, float* dst, const float* a, const float* b, int width, int height, int channels_d,
+                        int channels_s, int64_t stride_d, int64_t stride_s, void* stream)
+{
+    return pointwise(GF_PW_LINEAR, src, a, b, nullptr, dst, width, height, channels_d, channels_s, stride_d, stride_s, 0.f, stream, "gLinearTransform");
+}
+
+}  // extern "C"
+
+#include "gf_host.inl"

@@ -1,0 +1,113 @@
+// gf_host.inl -- host-buffer entry points (included at the end of gf_api.cu).
+//
+// gf_guided_gray_host is the end-to-end call: it uploads guide and src, filters, and downloads
+// dst, pipelined in row bands over three streams so that H2D of band b+1, the kernel of band b
+// and D2H of band b-1 overlap (PCIe is full duplex; the kernel is ~1% of the copy time).
+#include <mutex>
+
+#ifdef GF_CPU_EMU
+extern "C" {
+int gf_host_alloc(void** ptr, size_t bytes) { *ptr = std::malloc(bytes); return *ptr ? GF_OK : fail(GF_ERR_NOMEM, "malloc"); }
+int gf_host_free(void* ptr) { std::free(ptr); return GF_OK; }
+int gf_guided_gray_host(const float* guide, const float* src, float* dst, int width, int height, int r, float eps, int border)
+{
+    return gf_guided_gray(guide, src, dst, nullptr, nullptr, width, height, 0, 0, 0, 0, r, eps, border, nullptr);
+}
+}
+#else
+namespace {
+const int kMaxBands = 16;
+struct HostPipe {
+    std::mutex mu;
+    float* dev = nullptr;      // guide | src | dst planes
+    size_t cap = 0;            // floats per plane
+    cudaStream_t up = nullptr, comp = nullptr, down = nullptr;
+    cudaEvent_t ev_up[kMaxBands], ev_k[kMaxBands];
+    bool init = false;
+    int device = -1;
+};
+HostPipe g_pipe;
+
+#define GF_CU(call)                                                                  \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) return fail(GF_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+}  // namespace
+
+extern "C" {
+
+int gf_host_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) return fail(GF_ERR_INVALID, "null pointer");
+    GF_CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return GF_OK;
+}
+
+int gf_host_free(void* ptr)
+{
+    GF_CU(cudaFreeHost(ptr));
+    return GF_OK;
+}
+
+int gf_guided_gray_host(const float* guide, const float* src, float* dst, int width, int height, int r, float eps, int border)
+{
+    if (!guide || !src || !dst) return fail(GF_ERR_INVALID, "null image pointer");
+    if (width <= 0 || height <= 0 || r < 0) return fail(GF_ERR_INVALID, "bad geometry %dx%d r=%d", width, height, r);
+    HostPipe& P = g_pipe;
+    std::lock_guard<std::mutex> lock(P.mu);
+    int dev = 0;
+    GF_CU(cudaGetDevice(&dev));
+    if (!P.init || P.device != dev) {
+        GF_CU(cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
+        GF_CU(cudaStreamCreateWithFlags(&P.comp, cudaStreamNonBlocking));
+        GF_CU(cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxBands; ++i) {
+            GF_CU(cudaEventCreateWithFlags(&P.ev_up[i], cudaEventDisableTiming));
+            GF_CU(cudaEventCreateWithFlags(&P.ev_k[i], cudaEventDisableTiming));
+        }
+        P.init = true;
+        P.device = dev;
+        P.dev = nullptr;
+        P.cap = 0;
+    }
+    const size_t n = (size_t)width * height;
+    if (n > P.cap) {
+        if (P.dev) GF_CU(cudaFree(P.dev));
+        P.dev = nullptr;
+        P.cap = 0;
+        GF_CU(cudaMalloc((void**)&P.dev, 3 * n * sizeof(float)));
+        P.cap = n;
+    }
+    float *dI = P.dev, *dP = P.dev + P.cap, *dQ = P.dev + 2 * P.cap;
+    int nb = height / (4 * r + 64);
+    nb = nb < 1 ? 1 : (nb > 8 ? 8 : nb);
+    int up_to = 0;
+    for (int b = 0; b < nb; ++b) {
+        const int y0 = (int)((int64_t)height * b / nb), y1 = (int)((int64_t)height * (b + 1) / nb);
+        int need = y1 + 2 * r;
+        if (need > height || b == nb - 1) need = height;
+        if (need > up_to) {
+            const size_t off = (size_t)up_to * width, cnt = (size_t)(need - up_to) * width * sizeof(float);
+            GF_CU(cudaMemcpyAsync(dI + off, guide + off, cnt, cudaMemcpyHostToDevice, P.up));
+            GF_CU(cudaMemcpyAsync(dP + off, src + off, cnt, cudaMemcpyHostToDevice, P.up));
+            up_to = need;
+        }
+        GF_CU(cudaEventRecord(P.ev_up[b], P.up));
+        GF_CU(cudaStreamWaitEvent(P.comp, P.ev_up[b], 0));
+        // rows [0, up_to) are resident; the band reads at most rows [y0-2r, y1+2r) after mapping
+        int rc = gf_guided_gray_strip(dI, dP, dQ + (size_t)y0 * width, width, height, 0, up_to, y0, y1 - y0, width, width, width,
+                                      r, eps, border, P.comp);
+        if (rc) return rc;
+        GF_CU(cudaEventRecord(P.ev_k[b], P.comp));
+        GF_CU(cudaStreamWaitEvent(P.down, P.ev_k[b], 0));
+        GF_CU(cudaMemcpyAsync(dst + (size_t)y0 * width, dQ + (size_t)y0 * width, (size_t)(y1 - y0) * width * sizeof(float),
+                              cudaMemcpyDeviceToHost, P.down));
+    }
+    GF_CU(cudaStreamSynchronize(P.down));
+    GF_CU(cudaStreamSynchronize(P.comp));
+    return GF_OK;
+}
+
+}  // extern "C"
+#endif

@@ -1,0 +1,59 @@
+// gf_rt.h -- the few runtime calls the API layer needs, so that the same host logic builds
+// against the CUDA runtime (product) or the test-only SIMT emulator (tests/emu, -DGF_CPU_EMU).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef GF_CPU_EMU
+#include <cstdlib>
+#include <cstring>
+
+#include "cuda_emu.h"
+#define GF_LAUNCH(kernel, grid, block, smem, stream, ...) GF_EMU_LAUNCH(kernel, grid, block, smem, __VA_ARGS__)
+static inline const char* gf_rt_launch_error() { return nullptr; }
+template <class K> static inline const char* gf_rt_set_smem(K, size_t) { return nullptr; }
+static inline const char* gf_rt_alloc_async(void** p, size_t n, void*) { *p = std::malloc(n); return *p ? nullptr : "malloc failed"; }
+static inline void gf_rt_free_async(void* p, void*) { std::free(p); }
+static inline const char* gf_rt_copy2d_async(void* d, size_t dp, const void* s, size_t sp, size_t wb, size_t rows, void*)
+{
+    for (size_t y = 0; y < rows; ++y) std::memcpy((char*)d + y * dp, (const char*)s + y * sp, wb);
+    return nullptr;
+}
+static inline const char* gf_rt_device_info(int* sms, int* major, int* minor) { *sms = 4; *major = 0; *minor = 0; return nullptr; }
+static inline size_t gf_rt_max_smem() { return 200 * 1024; }
+#else
+#include <cuda_runtime.h>
+#define GF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+static inline const char* gf_rt_launch_error()
+{
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+template <class K> static inline const char* gf_rt_set_smem(K kernel, size_t bytes)
+{
+    if (bytes <= 48 * 1024) return nullptr;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+static inline const char* gf_rt_alloc_async(void** p, size_t n, void* stream)
+{
+    cudaError_t e = cudaMallocAsync(p, n, (cudaStream_t)stream);
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+static inline void gf_rt_free_async(void* p, void* stream) { cudaFreeAsync(p, (cudaStream_t)stream); }
+static inline const char* gf_rt_copy2d_async(void* d, size_t dp, const void* s, size_t sp, size_t wb, size_t rows, void* stream)
+{
+    cudaError_t e = cudaMemcpy2DAsync(d, dp, s, sp, wb, rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+static inline const char* gf_rt_device_info(int* sms, int* major, int* minor)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+static inline size_t gf_rt_max_smem() { return 227 * 1024; }
+#endif

@@ -1,0 +1,158 @@
+"""Two ways to drive the same C ABI from the tests:
+
+* CudaBackend -- the product library (libgf_b200.so) on a real GPU, device memory via torch.
+* EmuBackend  -- tests/emu/libgf_emu.so, the same kernels under the test-only SIMT emulator
+                 on host memory (numpy).  Only for kernel-logic tests without a GPU.
+
+Both expose the same helper methods and return numpy arrays, so parity cases are written once.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from cudaimageprocessing_b200._capi import GfApi
+
+
+class _Base:
+    api: GfApi
+
+    # --- memory helpers, overridden ---
+    def up(self, a: np.ndarray):
+        raise NotImplementedError
+
+    def empty(self, shape):
+        raise NotImplementedError
+
+    def ptr(self, buf) -> int:
+        raise NotImplementedError
+
+    def down(self, buf) -> np.ndarray:
+        raise NotImplementedError
+
+    def sync(self):
+        pass
+
+    # --- calls ---
+    def guided_gray(self, I, p, r, eps, border, want_ab=False, pad=0):
+        """pad > 0 gives every plane a row stride of width+pad floats (pitched layout)."""
+        h, w = I.shape
+        s = w + pad
+
+        def pitched(a):
+            b = np.zeros((h, s), np.float32)
+            b[:, :w] = a
+            return b
+        dI, dp = self.up(pitched(I)), self.up(pitched(p))
+        dq = self.empty((h, s))
+        dA = self.empty((h, s)) if want_ab else None
+        dB = self.empty((h, s)) if want_ab else None
+        self.api.call("gf_guided_gray", self.ptr(dI), self.ptr(dp), self.ptr(dq), self.ptr(dA) if want_ab else None,
+                      self.ptr(dB) if want_ab else None, w, h, s, s, s, s, r, eps, border, None)
+        self.sync()
+        q = self.down(dq)[:, :w]
+        if want_ab:
+            return q, self.down(dA)[:, :w], self.down(dB)[:, :w]
+        return q
+
+    def guided_color(self, I3, p, r, eps, border):
+        h, w, _ = I3.shape
+        pc = 1 if p.ndim == 2 else p.shape[2]
+        dI, dp = self.up(I3), self.up(p)
+        dq = self.empty(p.shape)
+        self.api.call("gf_guided_color", self.ptr(dI), self.ptr(dp), self.ptr(dq), w, h, pc, 0, 0, 0, r, eps, border, None)
+        self.sync()
+        return self.down(dq)
+
+    def class_run(self, I, p, r, eps, border=1):
+        h, w = I.shape[:2]
+        gch = 1 if I.ndim == 2 else I.shape[2]
+        sch = 1 if p.ndim == 2 else p.shape[2]
+        hnd = ctypes.c_void_p()
+        self.api.call("gf_create", ctypes.addressof(hnd), w, h, gch, sch)
+        try:
+            dI, dp = self.up(I), self.up(p)
+            dq = self.empty(p.shape)
+            self.api.call("gf_run", hnd, self.ptr(dI), self.ptr(dp), self.ptr(dq), r, eps, border, 0, 0, 0, None)
+            self.sync()
+            return self.down(dq)
+        finally:
+            self.api.call("gf_destroy", hnd)
+
+    def batch(self, I, p, r, eps, border):
+        n, h, w = p.shape
+        gch = 1 if I.ndim == 3 else I.shape[3]
+        dI, dp = self.up(I), self.up(p)
+        dq = self.empty(p.shape)
+        self.api.call("gf_guided_batch", self.ptr(dI), self.ptr(dp), self.ptr(dq), n, w, h, gch, 0, 0, 0, 0, 0, 0,
+                      r, eps, border, None)
+        self.sync()
+        return self.down(dq)
+
+    def strip(self, I_buf, p_buf, width, global_h, buf_y0, out_y0, out_rows, r, eps, border):
+        dI, dp = self.up(I_buf), self.up(p_buf)
+        dq = self.empty((out_rows, width))
+        self.api.call("gf_guided_gray_strip", self.ptr(dI), self.ptr(dp), self.ptr(dq), width, global_h, buf_y0,
+                      I_buf.shape[0], out_y0, out_rows, 0, 0, 0, r, eps, border, None)
+        self.sync()
+        return self.down(dq)
+
+    def box(self, a, r, border, inplace=False):
+        h, w = a.shape[:2]
+        c = 1 if a.ndim == 2 else a.shape[2]
+        d = self.up(a)
+        o = d if inplace else self.empty(a.shape)
+        self.api.call("gf_box_filter", self.ptr(d), self.ptr(o), w, h, c, 0, 0, r, border, None)
+        self.sync()
+        return self.down(o)
+
+    def pointwise(self, name, out_shape, *arrays, tail=()):
+        bufs = [self.up(a) for a in arrays]
+        o = self.empty(out_shape)
+        return bufs, o
+
+
+class EmuBackend(_Base):
+    name = "emu"
+
+    def __init__(self):
+        from emu.build_emu import build_emu
+        self.api = GfApi(ctypes.CDLL(build_emu()))
+
+    def up(self, a):
+        return np.ascontiguousarray(a, dtype=np.float32).copy()
+
+    def empty(self, shape):
+        return np.full(shape, np.nan, np.float32)
+
+    def ptr(self, buf):
+        return None if buf is None else buf.ctypes.data
+
+    def down(self, buf):
+        return buf
+
+
+class CudaBackend(_Base):
+    name = "cuda"
+
+    def __init__(self):
+        import torch
+        import cudaimageprocessing_b200 as pkg
+        self.torch = torch
+        self.api = pkg.api()
+
+    def up(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+    def empty(self, shape):
+        return self.torch.full(tuple(shape), float("nan"), dtype=self.torch.float32, device="cuda")
+
+    def ptr(self, buf):
+        return None if buf is None else buf.data_ptr()
+
+    def down(self, buf):
+        return buf.cpu().numpy()
+
+    def sync(self):
+        self.torch.cuda.synchronize()

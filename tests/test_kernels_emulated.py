@@ -1,0 +1,118 @@
+"""CPU tests of the KERNEL LOGIC: the product's CUDA kernels and API layer compiled against the
+test-only SIMT emulator (tests/emu) and compared with the oracle.  This checks indexing, halos,
+border rules, barriers and shuffles without a GPU; the -m gpu tests check the real thing.
+Sizes are tiny because every CUDA thread is a fiber."""
+import numpy as np
+import pytest
+
+from conftest import load_kat_crops, synth_pair
+from oracle import gf_oracle as O
+
+TOL = 1e-4   # north_star: max abs error <= 1e-4 on [0,1]-normalised float output
+
+
+@pytest.fixture(scope="module")
+def be():
+    from gf_backend import EmuBackend
+    return EmuBackend()
+
+
+@pytest.mark.parametrize("border", [0, 1, 2])
+@pytest.mark.parametrize("shape,r", [((1, 1), 1), ((3, 5), 2), ((20, 33), 1), ((37, 53), 4), ((24, 150), 5),
+                                     ((40, 70), 8), ((19, 23), 12)])
+def test_gray_generic(be, shape, r, border):
+    I, p = synth_pair(*shape, seed=11)
+    q = be.guided_gray(I, p, r, 1e-2, border)
+    ref = O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)
+    assert np.abs(q - ref).max() <= TOL
+    assert be.api.last_kernel().startswith("generic")
+
+
+@pytest.mark.parametrize("shape,r,border", [((20, 300), 8, 0), ((150, 40), 2, 1), ((70, 300), 6, 2),
+                                            ((30, 20), 60, 0), ((30, 20), 60, 1), ((12, 9), 20, 2)])
+def test_gray_generic_multi_cta(be, shape, r, border):
+    """several strips / several bands / the global-memory ring (r=60) / r far beyond the image."""
+    I, p = synth_pair(*shape, seed=21, kind="structured")
+    q = be.guided_gray(I, p, r, 1e-2, border)
+    assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
+
+
+def test_gray_ab_and_pitch(be):
+    I, p = synth_pair(30, 45, seed=2, kind="structured")
+    q, A, B = be.guided_gray(I, p, 3, 0.3, 0, want_ab=True, pad=7)
+    rq, ra, rb = O.guided_filter_gray(I, p, 3, 0.3, 0, np.float64, return_ab=True)
+    assert np.abs(q - rq).max() <= 1e-5 and np.abs(A - ra).max() <= 1e-4 and np.abs(B - rb).max() <= 1e-4
+
+
+def test_kat_crop_u8(be):
+    """A corner window of the reference's r=7 KAT through the emulated kernels: <= 1 LSB."""
+    crop = [c for c in load_kat_crops() if c["name"] == "tl"][0]
+    P, I = crop["P"][:60, :70], crop["I"][:60, :70]
+    q = be.guided_gray(I, P, 7, 0.3, 0)
+    gold = crop["gold"][:32, :42]     # rows/cols >= 2r away from the artificial cut
+    d = O.to_u8(q)[:32, :42].astype(int) - gold.astype(int)
+    assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 2
+
+
+@pytest.mark.parametrize("border", [0, 1])
+def test_color_generic(be, border):
+    rng = np.random.default_rng(4)
+    I3 = rng.random((22, 40, 3), dtype=np.float32)
+    p = rng.random((22, 40), dtype=np.float32)
+    q = be.guided_color(I3, p, 3, 1e-2, border)
+    assert np.abs(q - O.guided_filter_color(I3, p, 3, 1e-2, border)).max() <= TOL
+
+
+def test_class_run_channel_pairs(be):
+    rng = np.random.default_rng(6)
+    g1 = rng.random((18, 26), dtype=np.float32)
+    g3 = rng.random((18, 26, 3), dtype=np.float32)
+    s3 = rng.random((18, 26, 3), dtype=np.float32)
+    for I, p in ((g1, g1 * 0.5), (g3, s3), (g1, s3)):
+        q = be.class_run(I, p, 2, 0.05)
+        assert np.abs(q - O.guided_filter_class_run(I, p, 2, 0.05)).max() <= TOL
+    q = be.class_run(g3, g1, 2, 0.05)   # (3,1): colour guide
+    assert np.abs(q - O.guided_filter_color(g3, g1, 2, 0.05, O.BORDER_TRUNCATE)).max() <= TOL
+
+
+def test_batch_and_strips(be):
+    rng = np.random.default_rng(8)
+    I = rng.random((3, 20, 36), dtype=np.float32)
+    p = rng.random((3, 20, 36), dtype=np.float32)
+    q = be.batch(I, p, 2, 1e-2, 0)
+    for k in range(3):
+        assert np.abs(q[k] - O.guided_filter_gray(I[k], p[k], 2, 1e-2, 0)).max() <= TOL
+    # a 48-row image cut into 3 strips of 16 rows, each seeing only its rows + 2r halo
+    I, p = synth_pair(48, 40, seed=9)
+    r = 3
+    ref = O.guided_filter_gray(I, p, r, 1e-2, 0)
+    for s in range(3):
+        y0, y1 = 16 * s, 16 * (s + 1)
+        b0, b1 = max(0, y0 - 2 * r), min(48, y1 + 2 * r)
+        q = be.strip(I[b0:b1], p[b0:b1], 40, 48, b0, y0, 16, r, 1e-2, 0)
+        assert np.abs(q - ref[y0:y1]).max() <= TOL
+    with pytest.raises(Exception):      # halo rows missing -> refused, not silently wrong
+        be.strip(I[16:32], p[16:32], 40, 48, 16, 16, 16, r, 1e-2, 0)
+
+
+@pytest.mark.parametrize("c", [1, 3])
+@pytest.mark.parametrize("border", [0, 1])
+def test_box_filter(be, c, border):
+    rng = np.random.default_rng(12)
+    a = rng.random((21, 34, c), dtype=np.float32) if c > 1 else rng.random((21, 34), dtype=np.float32)
+    for r in (2, 6):
+        out = be.box(a, r, border)
+        assert np.abs(out - O.box_mean(a, r, border)).max() <= 2e-6
+    out = be.box(a, 2, border, inplace=True)
+    assert np.abs(out - O.box_mean(a, 2, border)).max() <= 2e-6
+
+
+def test_errors_are_loud(be):
+    from cudaimageprocessing_b200._capi import GfError
+    I, p = synth_pair(8, 8)
+    with pytest.raises(GfError):
+        be.guided_gray(I, p, -1, 1e-2, 0)
+    with pytest.raises(GfError):
+        be.guided_gray(I, p, 2, 1e-2, 7)
+    with pytest.raises(GfError):
+        be.class_run(np.zeros((4, 4, 2), np.float32), np.zeros((4, 4), np.float32), 1, 0.1)
