@@ -167,8 +167,7 @@ bool overlaps(const Plane& a, const Plane& b, int rows, int count)
 
 int run_job(const Job& j)
 {
-    int rc = check_common(j);
-    if (rc) return rc;
+    int rc = GF_OK;
     bool done = false;
 #ifdef GF_HAVE_FAST
     {
@@ -191,14 +190,14 @@ int run_job(const Job& j)
 int run_jobs(Job* js, int n)
 {
     const Job& j0 = js[0];
-    if (!j0.dst.ptr || !j0.guide.ptr || !j0.src.ptr) return fail(GF_ERR_INVALID, "null image pointer");
+    for (int i = 0; i < n; ++i)
+        if (int rc0 = check_common(js[i])) return rc0;     // refuse bad arguments before anything is allocated
     const bool alias = overlaps(j0.dst, j0.guide, j0.buf_rows, j0.count) || overlaps(j0.dst, j0.src, j0.buf_rows, j0.count);
     void* tmp = nullptr;
     const size_t row_bytes = (size_t)j0.width * j0.dst.channels * sizeof(float);
     const Plane user_dst = j0.dst;
     int rc = GF_OK;
     if (alias) {
-        if (j0.width <= 0 || j0.out_rows <= 0 || j0.count <= 0) return fail(GF_ERR_INVALID, "non-positive size");
         const size_t bytes = row_bytes * j0.out_rows * j0.count;
         if (const char* e = gf_rt_alloc_async(&tmp, bytes, j0.stream)) return fail(GF_ERR_NOMEM, "in-place temporary: %s", e);
         for (int i = 0; i < n; ++i) {

@@ -1,0 +1,92 @@
+// gf_shim.cu -- C++ drop-in layer: the reference's class GuidedFilter and h* launchers
+// (include/guided_filter.h, include/guided_filter_d.h) implemented on the C ABI.
+// Error behaviour mirrors the reference: unsupported channel combinations print and return
+// (guided_filter_d.cu:893,948,978,1008,1038); CUDA failures print and exit(-1) (cuda_utils.h).
+#include "../../include/gf_b200.h"
+#include "../../include/guided_filter.h"
+#include "../../include/guided_filter_d.h"
+
+namespace {
+void handle(int rc, const char* where)
+{
+    if (rc == GF_OK) return;
+    if (rc == GF_ERR_UNSUPPORTED) {
+        std::printf("%s\n", gf_last_error());
+        return;
+    }
+    std::fprintf(stderr, "%s failed: %s\n", where, gf_last_error());
+    std::exit(-1);
+}
+
+// the row stride cudaMallocPitch gives a (width*channels)-float row: the implicit contract of
+// the reference class (guided_filter.cpp:80-92)
+int pitch_floats(int width, int channels)
+{
+    void* p = nullptr;
+    size_t pitch = 0;
+    CHECK(cudaMallocPitch(&p, &pitch, (size_t)width * channels * sizeof(float), 1));
+    CHECK(cudaFree(p));
+    return (int)(pitch / sizeof(float));
+}
+}  // namespace
+
+GuidedFilter::GuidedFilter() {}
+
+GuidedFilter::~GuidedFilter()
+{
+    if (impl) gf_destroy(impl);
+    impl = nullptr;
+}
+
+void GuidedFilter::init(const int _width, const int _height, const int _guided_channel, const int _src_channel)
+{
+    if (impl) gf_destroy(impl);
+    impl = nullptr;
+    swhcs.w = _width; swhcs.x = _height; swhcs.y = _src_channel;
+    gwhcs.w = _width; gwhcs.x = _height; gwhcs.y = _guided_channel;
+    swhcs.z = pitch_floats(_width, _src_channel);
+    gwhcs.z = pitch_floats(_width, _guided_channel);
+    handle(gf_create(&impl, _width, _height, _guided_channel, _src_channel), "GuidedFilter::init");
+}
+
+void GuidedFilter::run(float* guidiance, float* src, float* dst, const int r, const float eps)
+{
+    if (!impl) {
+        std::printf("GuidedFilter::run called before a successful init\n");
+        return;
+    }
+    handle(gf_run(impl, guidiance, src, dst, r, eps, GF_BORDER_TRUNCATE, gwhcs.z, swhcs.z, swhcs.z, nullptr), "GuidedFilter::run");
+}
+
+void hBoxFilter(float* src, float* dst, float* /*integral*/, const int4& swhcs, const int4& /*iwhcs*/, const int r)
+{
+    handle(gf_box_filter(src, dst, swhcs.w, swhcs.x, swhcs.y, swhcs.z, swhcs.z, r, GF_BORDER_TRUNCATE, nullptr), "hBoxFilter");
+}
+
+void hMultiply(float* a, float* b, float* c, const int4& awhcs, const int4& bwhcs)
+{
+    handle(gf_multiply(a, b, c, awhcs.w, awhcs.x, awhcs.y, bwhcs.y, awhcs.z, bwhcs.z, nullptr), "hMultiply");
+}
+
+void hCalcA(float* a, float* pm, float* im, float* ipm, float* iim, const int4& swhcs, const int4& gwhcs, const float eps)
+{
+    handle(gf_calc_a(a, pm, im, ipm, iim, swhcs.w, swhcs.x, swhcs.y, gwhcs.y, swhcs.z, gwhcs.z, eps, nullptr), "hCalcA");
+}
+
+void hCalcB(float* b, float* a, float* pm, float* im, const int4& swhcs, const int4& gwhcs)
+{
+    handle(gf_calc_b(b, a, pm, im, swhcs.w, swhcs.x, swhcs.y, gwhcs.y, swhcs.z, gwhcs.z, nullptr), "hCalcB");
+}
+
+void hLinearTransform(float* src, float* dst, float* a, float* b, const int4& swhcs, const int4& dwhcs)
+{
+    handle(gf_linear_transform(src, dst, a, b, dwhcs.w, dwhcs.x, dwhcs.y, swhcs.y, dwhcs.z, swhcs.z, nullptr), "hLinearTransform");
+}
+
+void hGuidedFilter(float* d_guided, float* d_src, float* d_dst, float* d_A, float* d_B, float eps, int radius, int width,
+                   int height, int stride)
+{
+    handle(gf_guided_gray(d_guided, d_src, d_dst, d_A, d_B, width, height, stride, stride, stride, stride, radius, eps,
+                          GF_BORDER_REFLECT101, nullptr),
+           "hGuidedFilter");
+}

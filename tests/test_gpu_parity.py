@@ -1,0 +1,258 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the C ABI
+of libgf_b200.so on device memory and is compared with the CPU oracle on the same inputs:
+float output within 1e-4 of the float64 restatement (north_star), the reference's own r=7 KAT
+at the uint8 level, and size-independent properties at BASELINE.json's full sizes."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_kat_crops, load_kat_full, synth_pair
+from oracle import c_oracle as C
+from oracle import gf_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def be():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from gf_backend import CudaBackend
+    b = CudaBackend()
+    sms, major, minor = b.api.device_info()
+    print(f"device: {sms} SMs, cc {major}.{minor}")
+    return b
+
+
+NT = max(1, (os.cpu_count() or 2) - 1)
+
+
+@pytest.mark.parametrize("border", [0, 1, 2])
+@pytest.mark.parametrize("shape,r", [((1, 1), 1), ((3, 5), 2), ((37, 53), 4), ((257, 129), 7), ((129, 257), 8),
+                                     ((300, 1000), 16), ((64, 48), 40), ((500, 333), 32), ((97, 1031), 1),
+                                     ((211, 307), 0), ((90, 70), 100)])
+def test_gray_small_vs_oracle(be, shape, r, border):
+    I, p = synth_pair(*shape, seed=31)
+    q = be.guided_gray(I, p, r, 1e-2, border)
+    ref = C.guided_gray_f64(I, p, r, 1e-2, border, NT)
+    assert np.abs(q - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("kind", ["noise", "structured"])
+@pytest.mark.parametrize("border", [0, 1])
+def test_gray_4k_r8(be, kind, border):
+    """BASELINE config 2: 3840x2160 gray, r=8, eps=1e-2."""
+    I, p = synth_pair(2160, 3840, seed=0, kind=kind)
+    q, A, B = be.guided_gray(I, p, 8, 1e-2, border, want_ab=True)
+    ref = C.guided_gray_f64(I, p, 8, 1e-2, border, NT)
+    err = np.abs(q - ref).max()
+    print(f"4K r=8 {kind} border={border}: kernel={be.api.last_kernel()} max err {err:.3e}")
+    assert err <= TOL
+    q2 = be.guided_gray(I, p, 8, 1e-2, border)               # without A/B outputs: identical q
+    assert np.array_equal(q, q2)
+    if border == 0:
+        _, ra, rb = C.guided_gray_f32(I, p, 8, 1e-2, 0, NT, return_ab=True)
+        assert np.abs(A - ra).max() <= 2e-4 and np.abs(B - rb).max() <= 2e-4
+
+
+def test_kat_full_frame_u8(be):
+    """The reference's KAT (r=7, eps=0.3, main.cpp:193-304): our q, converted like
+    main.cpp:296, against data/adobe_image_4_myres.png.  The reference's own GPU result differs
+    from that PNG in 34 px by 1 LSB; we allow the same class of knife-edge differences."""
+    k = load_kat_full()
+    q = be.guided_gray(k["I"], k["P"], k["r"], k["eps"], 0)
+    d = O.to_u8(q).astype(int) - k["gold"].astype(int)
+    n = int(np.count_nonzero(d))
+    print(f"KAT: {n} px differ from _myres.png (reference GPU: 34), max {np.abs(d).max()} LSB")
+    assert np.abs(d).max() <= 1 and n <= 83          # 0.001 % of 8 294 400
+    q64 = C.guided_gray_f64(k["I"], k["P"], k["r"], k["eps"], 0, NT)
+    assert np.abs(q - q64).max() <= 1e-5
+
+
+@pytest.mark.parametrize("crop", load_kat_crops(), ids=lambda c: c["name"])
+def test_kat_crops_u8(be, crop):
+    oy, ox = crop["off"]
+    n = crop["gold"].shape[0]
+    q = be.guided_gray(crop["I"], crop["P"], 7, 0.3, 0)
+    d = O.to_u8(q)[oy:oy + n, ox:ox + n].astype(int) - crop["gold"].astype(int)
+    assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 2
+
+
+@pytest.mark.parametrize("border", [0, 1])
+def test_color_1080p_r16(be, border):
+    """BASELINE config 3 frame: 1920x1080 RGB guide, 1-channel src, r=16, eps=1e-2."""
+    I3 = np.random.default_rng(100).random((1080, 1920, 3), dtype=np.float32)
+    p = np.random.default_rng(10000).random((1080, 1920), dtype=np.float32)
+    q = be.guided_color(I3, p, 16, 1e-2, border)
+    ref = C.guided_color_f32(I3, p, 16, 1e-2, border, NT)
+    err = np.abs(q - ref).max()
+    print(f"colour 1080p r=16 border={border}: max err {err:.3e}")
+    assert err <= TOL
+
+
+def test_color_small_and_3ch_src(be):
+    rng = np.random.default_rng(4)
+    I3 = rng.random((70, 95, 3), dtype=np.float32)
+    p3 = rng.random((70, 95, 3), dtype=np.float32)
+    for r, border in ((3, 0), (9, 1), (5, 2)):
+        q = be.guided_color(I3, p3, r, 1e-2, border)
+        assert np.abs(q - O.guided_filter_color(I3, p3, r, 1e-2, border)).max() <= TOL
+
+
+def test_gray_8k_r32(be):
+    """BASELINE config 4: 7680x4320 gray, r=32."""
+    I, p = synth_pair(4320, 7680, seed=0)
+    q = be.guided_gray(I, p, 32, 1e-2, 0)
+    ref = C.guided_gray_f64(I, p, 32, 1e-2, 0, NT)
+    err = np.abs(q - ref).max()
+    print(f"8K r=32: kernel={be.api.last_kernel()} max err {err:.3e}")
+    assert err <= TOL
+
+
+def test_class_run_channel_pairs(be):
+    rng = np.random.default_rng(6)
+    g1 = rng.random((180, 260), dtype=np.float32)
+    g3 = rng.random((180, 260, 3), dtype=np.float32)
+    s3 = rng.random((180, 260, 3), dtype=np.float32)
+    for I, p in ((g1, g1 * 0.5), (g3, s3), (g1, s3)):
+        q = be.class_run(I, p, 7, 0.3)
+        assert np.abs(q - O.guided_filter_class_run(I, p, 7, 0.3)).max() <= TOL
+    q = be.class_run(g3, g1, 5, 0.05)
+    assert np.abs(q - O.guided_filter_color(g3, g1, 5, 0.05, O.BORDER_TRUNCATE)).max() <= TOL
+
+
+def test_batch_matches_single(be):
+    rng = np.random.default_rng(8)
+    I = rng.random((5, 270, 480, 3), dtype=np.float32)
+    p = rng.random((5, 270, 480), dtype=np.float32)
+    q = be.batch(I, p, 16, 1e-2, 0)
+    for k in (0, 4):
+        assert np.abs(q[k] - O.guided_filter_color(I[k], p[k], 16, 1e-2, 0)).max() <= TOL
+    Ig = rng.random((4, 200, 300), dtype=np.float32)
+    q = be.batch(Ig, p[:4, :200, :300].copy(), 8, 1e-2, 1)
+    for k in range(4):
+        assert np.abs(q[k] - O.guided_filter_gray(Ig[k], p[k, :200, :300], 8, 1e-2, 1)).max() <= TOL
+
+
+def test_strips_equal_whole(be):
+    """Row-strip sharding (BASELINE config 5) on one GPU: 8 strips, each given only its rows plus
+    the 2r halo a neighbour would send, reproduce the whole-image result BIT-exactly?  No --
+    band boundaries change summation order; we require <= 1e-6 between the two and <= 1e-4 to
+    the oracle."""
+    I, p = synth_pair(1024, 2048, seed=7)
+    r = 16
+    whole = be.guided_gray(I, p, r, 1e-2, 0)
+    ref = C.guided_gray_f64(I, p, r, 1e-2, 0, NT)
+    assert np.abs(whole - ref).max() <= TOL
+    G = 8
+    for s in range(G):
+        y0, y1 = 1024 * s // G, 1024 * (s + 1) // G
+        b0, b1 = max(0, y0 - 2 * r), min(1024, y1 + 2 * r)
+        q = be.strip(I[b0:b1], p[b0:b1], 2048, 1024, b0, y0, y1 - y0, r, 1e-2, 0)
+        assert np.abs(q - ref[y0:y1]).max() <= TOL
+        assert np.abs(q - whole[y0:y1]).max() <= 2e-6
+
+
+def test_properties_at_full_size(be):
+    """Size-independent properties on the 4K frame: linearity in p for a fixed guide, shift
+    invariance, constant reproduction, and eps -> 0 self-guidance returning the input."""
+    I, p1 = synth_pair(2160, 3840, seed=3)
+    _, p2 = synth_pair(2160, 3840, seed=5)
+    q1 = be.guided_gray(I, p1, 8, 1e-2, 0)
+    q2 = be.guided_gray(I, p2, 8, 1e-2, 0)
+    q12 = be.guided_gray(I, (0.25 * p1 + 0.5 * p2).astype(np.float32), 8, 1e-2, 0)
+    assert np.abs(q12 - (0.25 * q1 + 0.5 * q2)).max() <= 2e-5
+    qs = be.guided_gray(I, (p1 * 0.5 + 0.25).astype(np.float32), 8, 1e-2, 0)
+    assert np.abs(qs - (0.5 * q1 + 0.25)).max() <= 2e-5
+    c = np.full_like(I, 0.625)
+    assert np.abs(be.guided_gray(I, c, 8, 1e-2, 1) - 0.625).max() <= 2e-5
+    qi = be.guided_gray(I, I, 8, 1e-7, 0)
+    assert np.abs(qi - I).max() <= 2e-3       # a -> 1, b -> 0 where var >> eps
+
+
+@pytest.mark.parametrize("c", [1, 3])
+def test_box_filter(be, c):
+    rng = np.random.default_rng(12)
+    a = rng.random((300, 500, c), dtype=np.float32) if c > 1 else rng.random((300, 500), dtype=np.float32)
+    for r, border in ((7, 1), (16, 0), (2, 2)):
+        assert np.abs(be.box(a, r, border) - O.box_mean(a, r, border)).max() <= 2e-6
+    assert np.abs(be.box(a, 7, 1, inplace=True) - O.box_mean(a, 7, 1)).max() <= 2e-6
+
+
+def test_host_entry_and_dropin_program(be, tmp_path):
+    """gf_guided_gray_host (the e2e call) and the C++ program written against the reference's
+    headers (tests/dropin/dropin_demo.cpp) produce the oracle's answer."""
+    I, p = synth_pair(600, 800, seed=13)
+    q = np.empty_like(I)
+    be.api.call("gf_guided_gray_host", I.ctypes.data, p.ctypes.data, q.ctypes.data, 800, 600, 8, 1e-2, 0)
+    assert np.abs(q - C.guided_gray_f64(I, p, 8, 1e-2, 0, NT)).max() <= TOL
+
+    lib_dir = os.path.join(ROOT, "cudaimageprocessing_b200")
+    exe = tmp_path / "dropin_demo"
+    subprocess.check_call(["nvcc", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "dropin", "dropin_demo.cpp"), "-o", str(exe),
+                           "-L", lib_dir, "-lgf_b200", "-Xlinker", "-rpath=" + lib_dir])
+    w, h, r, sch, eps = 333, 217, 7, 3, 0.3
+    rng = np.random.default_rng(2)
+    g = rng.random((h, w), dtype=np.float32)
+    s = rng.random((h, w, sch), dtype=np.float32)
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([w, h, r, sch], np.int32).tobytes())
+        f.write(np.float32(eps).tobytes())
+        f.write(g.tobytes())
+        f.write(s.tobytes())
+    subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    out = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
+    n = w * h
+    q_class = out[:n * sch].reshape(h, w, sch)
+    q_fused, A, B = (out[n * sch + i * n: n * sch + (i + 1) * n].reshape(h, w) for i in range(3))
+    assert np.abs(q_class - O.guided_filter_class_run(g, s, r, eps)).max() <= TOL
+    rq, ra, rb = O.guided_filter_gray(g, s[:, :, 0], r, eps, 0, np.float64, return_ab=True)
+    assert np.abs(q_fused - rq).max() <= TOL and np.abs(A - ra).max() <= TOL and np.abs(B - rb).max() <= TOL
+
+
+def test_against_reference_gpu_code(be):
+    """The reference's own GPU sources, compiled unmodified for sm_100a (oracle/_ref): path B
+    (hGuidedFilter, r=7) agrees with us to float rounding; path A's float32 integral image is
+    reported beside ours (it is ~1e-2 off at 4K)."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libgfref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libgfref.so not built")
+    import torch
+    ref = ctypes.CDLL(so)
+    fp = ctypes.c_void_p
+    ref.gfref_hguided.argtypes = [fp, fp, fp, fp, fp, ctypes.c_float] + [ctypes.c_int] * 4
+    ref.gfref_create.restype = ctypes.c_void_p
+    ref.gfref_create.argtypes = [ctypes.c_int] * 4
+    ref.gfref_run.argtypes = [fp, fp, fp, fp, ctypes.c_int, ctypes.c_float]
+    ref.gfref_destroy.argtypes = [fp]
+    ref.gfref_pitch_floats.argtypes = [ctypes.c_int] * 3
+    h, w = 2160, 3840
+    I, p = synth_pair(h, w, seed=0)
+    dI, dp = torch.from_numpy(I).cuda(), torch.from_numpy(p).cuda()
+    dq, dA, dB = torch.zeros_like(dI), torch.zeros_like(dI), torch.zeros_like(dI)
+    ref.gfref_hguided(dI.data_ptr(), dp.data_ptr(), dq.data_ptr(), dA.data_ptr(), dB.data_ptr(), 0.3, 7, w, h, w)
+    torch.cuda.synchronize()
+    ours = be.guided_gray(I, p, 7, 0.3, 0)
+    o64 = C.guided_gray_f64(I, p, 7, 0.3, 0, NT)
+    e_ref, e_ours = np.abs(dq.cpu().numpy() - o64).max(), np.abs(ours - o64).max()
+    print(f"path B r=7 4K: |ref_gpu - f64| = {e_ref:.3e}, |ours - f64| = {e_ours:.3e}")
+    assert e_ours <= TOL and np.abs(ours - dq.cpu().numpy()).max() <= 1e-4
+    # path A (class, TRUNCATE border), r=8: needs cudaMallocPitch-compatible strides
+    stride = ref.gfref_pitch_floats(w, 1, h)
+    assert stride == w, "4K rows are already pitch-aligned"
+    g = ref.gfref_create(w, h, 1, 1)
+    dq.zero_()
+    ref.gfref_run(g, dI.data_ptr(), dp.data_ptr(), dq.data_ptr(), 8, 1e-2)
+    torch.cuda.synchronize()
+    ref.gfref_destroy(g)
+    oursA = be.class_run(I, p, 8, 1e-2)
+    o64 = C.guided_gray_f64(I, p, 8, 1e-2, 1, NT)
+    e_ref, e_ours = np.abs(dq.cpu().numpy() - o64).max(), np.abs(oursA - o64).max()
+    print(f"path A r=8 4K: |ref_gpu - f64| = {e_ref:.3e} (float32 integral image), |ours - f64| = {e_ours:.3e}")
+    assert e_ours <= TOL
