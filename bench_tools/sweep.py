@@ -1,0 +1,67 @@
+"""Timing sweeps on the GPU box (developer tool, not part of the product or the tests).
+    python bench_tools/sweep.py [case ...]
+"""
+import ctypes
+import itertools
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cudaimageprocessing_b200 as pkg  # noqa: E402
+
+api = pkg.api()
+
+
+def time_gray(w, h, r, nsets=6, iters=60, border=0, env=None):
+    for k, v in (env or {}).items():
+        os.environ[k] = str(v)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sets = [(torch.rand((h, w), device="cuda", generator=g), torch.rand((h, w), device="cuda", generator=g),
+             torch.empty((h, w), device="cuda")) for _ in range(nsets)]
+    s = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(s.cuda_stream)
+
+    def run(i):
+        a, b, c = sets[i % nsets]
+        api.call("gf_guided_gray", a.data_ptr(), b.data_ptr(), c.data_ptr(), None, None, w, h, 0, 0, 0, 0, r, 1e-2, border, sp)
+    for i in range(5):
+        run(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for i in range(iters):
+        run(i)
+    e1.record(s)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    for k in (env or {}):
+        os.environ.pop(k, None)
+    return {"w": w, "h": h, "r": r, "kernel": api.last_kernel(), "us": ms * 1e3, "gpix_s": w * h / ms / 1e6,
+            "gbs_alg": 12.0 * w * h / ms / 1e6, "env": env or {}}
+
+
+def main():
+    out = []
+    cases = sys.argv[1:] or ["4k"]
+    if "4k" in cases:
+        for cps, hbm in itertools.product([1, 2, 3, 4, 6], [24, 48, 96, 160]):
+            out.append(time_gray(3840, 2160, 8, env={"GF_FAST_CTAS_PER_SM": cps, "GF_FAST_HB_MIN": hbm}))
+            print(json.dumps(out[-1]), flush=True)
+        out.append(time_gray(3840, 2160, 8, env={"GF_DISABLE_FAST": 1}))
+        print(json.dumps(out[-1]), flush=True)
+    if "sizes" in cases:
+        for (w, h, r) in [(1920, 1080, 8), (1920, 1080, 16), (3840, 2160, 4), (3840, 2160, 7), (3840, 2160, 16), (7680, 4320, 8),
+                          (7680, 4320, 16), (7680, 4320, 32), (16384, 8192, 16)]:
+            out.append(time_gray(w, h, r, nsets=3 if w * h > 3e7 else 6, iters=20))
+            print(json.dumps(out[-1]), flush=True)
+    with open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

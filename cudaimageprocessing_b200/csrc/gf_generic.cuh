@@ -15,11 +15,12 @@
 // to shared memory; a window is  pre[x+r] - pre[x-r-1] + (totals of the chunks in between).
 // Partial sums never exceed 32*(2r+1) terms' worth, which keeps float32 error ~1e-7 relative
 // after the 1/(2r+1)^2 normalisation (the reference's float32 integral image loses 1e-2 at 4K,
-// SURVEY fact 4).  For r <= 4 the window is summed directly.
+// SURVEY fact 4).  For r <= GF_DIRECT_R the window is summed directly (pure additions: the
+// reference's fused path range r <= 7 keeps its ~1e-7 accuracy, which the uint8-level KAT needs).
 #pragma once
 #include "gf_common.cuh"
 
-#define GF_DIRECT_R 4
+#define GF_DIRECT_R 8
 
 // ---------------------------------------------------------------------------------------------
 // Horizontal (2r+1)-window sums of NQ per-thread values across the CTA's threads.

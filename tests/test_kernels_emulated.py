@@ -116,3 +116,50 @@ def test_errors_are_loud(be):
         be.guided_gray(I, p, 2, 1e-2, 7)
     with pytest.raises(GfError):
         be.class_run(np.zeros((4, 4, 2), np.float32), np.zeros((4, 4), np.float32), 1, 0.1)
+
+
+# ---- the tuned kernel (gf_fast.cuh) under the emulator -------------------------------------------
+@pytest.mark.parametrize("border", [0, 1, 2])
+@pytest.mark.parametrize("shape,r", [((20, 64), 1), ((24, 100), 2), ((30, 40), 3), ((20, 520), 4), ((26, 36), 5),
+                                     ((20, 48), 6), ((40, 133), 7), ((40, 600), 8), ((30, 64), 12), ((44, 500), 16)])
+def test_gray_fast(be, shape, r, border):
+    """widths with w % 4 == 0 take the tuned kernel (128-bit row alignment); several strips
+    (w > 480), warp-edge mailbox (every CTA has 4 warps), partial right edge, all borders."""
+    I, p = synth_pair(*shape, seed=41, kind="structured")
+    w = shape[1]
+    q = be.guided_gray(I, p, r, 1e-2, border, pad=(-w) % 4)
+    assert be.api.last_kernel() == f"fast_r{r}"
+    ref = O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)
+    assert np.abs(q - ref).max() <= TOL
+
+
+def test_gray_fast_ab_batch_strip(be):
+    I, p = synth_pair(36, 64, seed=5)
+    q, A, B = be.guided_gray(I, p, 4, 0.05, 0, want_ab=True)
+    assert be.api.last_kernel() == "fast_r4"
+    rq, ra, rb = O.guided_filter_gray(I, p, 4, 0.05, 0, np.float64, return_ab=True)
+    assert np.abs(q - rq).max() <= 1e-5 and np.abs(A - ra).max() <= 1e-4 and np.abs(B - rb).max() <= 1e-4
+    rng = np.random.default_rng(8)
+    Ib = rng.random((3, 20, 36), dtype=np.float32)
+    pb = rng.random((3, 20, 36), dtype=np.float32)
+    qb = be.batch(Ib, pb, 2, 1e-2, 1)
+    assert be.api.last_kernel() == "fast_r2"
+    for k in range(3):
+        assert np.abs(qb[k] - O.guided_filter_gray(Ib[k], pb[k], 2, 1e-2, 1)).max() <= TOL
+    I, p = synth_pair(48, 40, seed=9)
+    ref = O.guided_filter_gray(I, p, 3, 1e-2, 0)
+    for s in range(3):
+        y0, y1 = 16 * s, 16 * (s + 1)
+        b0, b1 = max(0, y0 - 6), min(48, y1 + 6)
+        qs = be.strip(I[b0:b1], p[b0:b1], 40, 48, b0, y0, 16, 3, 1e-2, 0)
+        assert be.api.last_kernel() == "fast_r3"
+        assert np.abs(qs - ref[y0:y1]).max() <= TOL
+
+
+def test_kat_crop_u8_fast(be):
+    crop = [c for c in load_kat_crops() if c["name"] == "tl"][0]
+    P, I = crop["P"][:60, :72], crop["I"][:60, :72]
+    q = be.guided_gray(I, P, 7, 0.3, 0)
+    assert be.api.last_kernel() == "fast_r7"
+    d = O.to_u8(q)[:32, :44].astype(int) - crop["gold"][:32, :44].astype(int)
+    assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 2
