@@ -54,6 +54,9 @@ def main():
             print(json.dumps(out[-1]), flush=True)
         out.append(time_gray(3840, 2160, 8, env={"GF_DISABLE_FAST": 1}))
         print(json.dumps(out[-1]), flush=True)
+    if "one" in cases:
+        out.append(time_gray(3840, 2160, 8, iters=6))
+        print(json.dumps(out[-1]), flush=True)
     if "sizes" in cases:
         for (w, h, r) in [(1920, 1080, 8), (1920, 1080, 16), (3840, 2160, 4), (3840, 2160, 7), (3840, 2160, 16), (7680, 4320, 8),
                           (7680, 4320, 16), (7680, 4320, 32), (16384, 8192, 16)]:

@@ -163,3 +163,13 @@ def test_kat_crop_u8_fast(be):
     assert be.api.last_kernel() == "fast_r7"
     d = O.to_u8(q)[:32, :44].astype(int) - crop["gold"][:32, :44].astype(int)
     assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 2
+
+
+@pytest.mark.parametrize("shape,r,border", [((24, 1452), 4, 0), ((40, 1400), 8, 1), ((34, 1400), 7, 2), ((60, 1100), 16, 0)])
+def test_gray_fast_steady_path(be, shape, r, border):
+    """wide enough for a CTA strictly inside the image and tall enough for the straight-line
+    steady-state loop (interior rows, 128-bit loads, constant normalisation) to run."""
+    I, p = synth_pair(*shape, seed=51)
+    q = be.guided_gray(I, p, r, 1e-2, border)
+    assert be.api.last_kernel() == f"fast_r{r}"
+    assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
