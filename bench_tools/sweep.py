@@ -46,12 +46,16 @@ def time_gray(w, h, r, nsets=6, iters=60, border=0, env=None):
 
 
 def main():
+    if __name__ != "__main__":
+        return
     out = []
     cases = sys.argv[1:] or ["4k"]
     if "4k" in cases:
-        for cps, hbm in itertools.product([1, 2, 3, 4, 6], [24, 48, 96, 160]):
-            out.append(time_gray(3840, 2160, 8, env={"GF_FAST_CTAS_PER_SM": cps, "GF_FAST_HB_MIN": hbm}))
+        for wps, hbm in itertools.product([4, 8, 12, 16], [32, 48, 64, 96, 136]):
+            out.append(time_gray(3840, 2160, 8, env={"GF_WP_WARPS_PER_SM": wps, "GF_WP_HB_MIN": hbm}))
             print(json.dumps(out[-1]), flush=True)
+        out.append(time_gray(3840, 2160, 8, env={"GF_DISABLE_WP": 1}))
+        print(json.dumps(out[-1]), flush=True)
         out.append(time_gray(3840, 2160, 8, env={"GF_DISABLE_FAST": 1}))
         print(json.dumps(out[-1]), flush=True)
     if "one" in cases:

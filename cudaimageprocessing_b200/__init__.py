@@ -22,7 +22,9 @@ def api() -> GfApi:
     global _API
     if _API is None:
         from .build import build
-        path = build()
+        # GF_LIB_PATH: developer switch for A/B-testing differently compiled builds of the SAME
+        # sources (bench_tools/); it must still be a libgf_b200 build -- there is no other backend.
+        path = os.environ.get("GF_LIB_PATH") or build()
         _API = GfApi(ctypes.CDLL(path))
     return _API
 

@@ -17,6 +17,7 @@
 #include "gf_rt.h"
 #ifdef GF_HAVE_FAST
 #include "gf_fast.cuh"
+#include "gf_wp.cuh"
 #endif
 
 namespace {
@@ -172,7 +173,8 @@ int run_job(const Job& j)
 #ifdef GF_HAVE_FAST
     {
         const char* name = nullptr;
-        const char* e = gf_fast_try(j, &done, &name);
+        const char* e = gf_wp_try(j, &done, &name);
+        if (!done) e = gf_fast_try(j, &done, &name);
         if (done) {
             if (e) rc = fail(GF_ERR_CUDA, "%s launch: %s", name, e);
             else { rc = GF_OK; g_launches++; g_kernel = name; }

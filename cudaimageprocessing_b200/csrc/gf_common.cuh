@@ -13,6 +13,13 @@
     T* name = reinterpret_cast<T*>(name##_raw_)
 #endif
 
+// L2 prefetch hint (no registers, no scoreboard): rows a few iterations ahead of the loads.
+#ifdef GF_CPU_EMU
+static inline void gf_prefetch_l2(const void*) {}
+#else
+__device__ __forceinline__ void gf_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 #define GF_REFLECT101 0
 #define GF_TRUNCATE 1
 #define GF_REFLECT 2

@@ -1,0 +1,369 @@
+// gf_wp.cuh -- warp-private fused guided-filter kernel for small radii (R <= 8), gray float32.
+//
+// Same arithmetic as gf_fast.cuh (4 adjacent columns per thread, block prefix/suffix window
+// sums over warp shuffles, stage-2 row ring in shared memory, rows prefetched one iteration
+// ahead) but every WARP is an independent worker: it owns a 128-column window of which the
+// middle 32-4*H1 lanes (96 columns at R=8) produce output, and a band of rows.  Nothing is
+// exchanged between warps, so the kernel has no barrier at all, warps drift freely (latency
+// hiding without extra warps) and the ring is only 2*(2R+1) float4 per OUTPUT lane, which lets
+// 16 warps live on an SM.  The 25% redundant lanes are L1/L2 hits and cheap FADDs; what they buy
+// back is the barrier stall that dominated the exchange version (profiles/).
+//
+// The row loop is cut into phases with compile-time stage flags so that a warp whose band and
+// columns are interior runs straight-line code: no border mapping, no predicates on t, constant
+// normalisation.  Border warps (first/last band, first/last strip) run the generic body.
+#pragma once
+#include "gf_fast.cuh"
+
+#ifndef GF_WP_PREFETCH
+#define GF_WP_PREFETCH 0      // rows ahead for an L2 prefetch hint; measured: no gain on B200 (0 = off)
+#endif
+
+template <int R>
+struct GfWpGeom {
+    static constexpr int H1 = GfFastGeom<R>::H1;
+    static constexpr int VL = 32 - 4 * H1;          // lanes that produce output
+    static constexpr int WOUT = 4 * VL;             // output columns per warp
+    static constexpr int KW = 2 * R + 1;
+    static constexpr int RING_CELLS = VL + 1;       // + one dump cell shared by the halo lanes
+    static constexpr size_t ring_bytes_per_warp = (size_t)KW * 2 * RING_CELLS * 16;
+};
+
+struct GfWpArgs {
+    const float* guide; const float* src; float* dst; float* A; float* B;
+    int64_t gs, ss, ds, abs_;
+    int64_t gfs, sfs, dfs, abfs;
+    int width, height, buf_y0, out_y0, out_rows, border, hb;
+    int nstrips, nbands, count;
+    float eps;
+};
+
+template <int R>
+struct GfWpCtx {
+    const float* gI; const float* gP; float* gQ; float* gA; float* gB;   // frame bases at column x0
+    int64_t gs, ss, ds, abs_;
+    float4* ring;            // this lane's ring cells: ring[(slot*2+q)*RING_CELLS]
+    int lane, x0, width, height, border, buf_y0, out_y0, yo0, yo1;
+    bool vec_ok, trunc, s1_lane, out_lane, has_ab;
+    float eps, inv_k;
+    float inv_nx[4];
+    bool x_in[4];
+    int sx[4];
+    float cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], va[4], vb[4];
+    float nI[4], nP[4], oI[4], oP[4], ctr[4];
+    int slot;
+};
+
+template <int R>
+__device__ __forceinline__ void gf_wp_ld(const GfWpCtx<R>& c, const float* base, int64_t stride, int row, float (&v)[4])
+{
+    if (row < 0) { v[0] = v[1] = v[2] = v[3] = 0.f; return; }
+    const float* p = base + (int64_t)row * stride;
+    if (c.vec_ok) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = c.sx[j] >= 0 ? p[c.sx[j] - c.x0] : 0.f;
+    }
+}
+
+__device__ __forceinline__ void gf_wp_ldv(const float* p, float (&v)[4])
+{
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+
+// Iteration t.  PH selects which stages are compiled in:
+//   0  t in [0, 2R)        vertical add only
+//   2  t in (2R, 4R)       stage 2 without output + stage 1 with subtraction
+//   3  t in (4R, steps)    everything (steady state)
+//   5  any t               generic: run-time stage flags, border mapping, masks
+// PH 0/2/3 require an INTERIOR warp: all rows and columns it touches are inside the image.
+template <int PH, int R>
+__device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
+{
+    using W = GfWpGeom<R>;
+    constexpr int KW = W::KW, RC = W::RING_CELLS;
+    constexpr bool GEN = PH == 5;
+    const int yi = c.yo0 - 2 * R + t;
+    const int lane = c.lane;
+    const bool a_on = GEN ? (t - 1 >= 2 * R) : (PH >= 2);
+    const bool out_on = GEN ? (t - 1 >= 4 * R) : (PH == 3);
+    const bool sub_on = GEN ? (t >= KW) : (PH >= 2);
+    const bool s1_on = GEN ? (t >= 2 * R) : (PH >= 2);
+
+    // ================= phase A: stage 2 of centre row yi-1-R =================
+    if (a_on) {
+        float hA[4], hB[4];
+        gf_window<R>(c.va, hA, lane);
+        gf_window<R>(c.vb, hB, lane);
+        float4* ca = c.ring + (size_t)(c.slot * 2 + 0) * RC;
+        float4* cb = c.ring + (size_t)(c.slot * 2 + 1) * RC;
+        const float4 oa = *ca, ob = *cb;
+        c.sA[0] += hA[0] - oa.x; c.sA[1] += hA[1] - oa.y; c.sA[2] += hA[2] - oa.z; c.sA[3] += hA[3] - oa.w;
+        c.sB[0] += hB[0] - ob.x; c.sB[1] += hB[1] - ob.y; c.sB[2] += hB[2] - ob.z; c.sB[3] += hB[3] - ob.w;
+        *ca = make_float4(hA[0], hA[1], hA[2], hA[3]);
+        *cb = make_float4(hB[0], hB[1], hB[2], hB[3]);
+        c.slot = c.slot + 1 == KW ? 0 : c.slot + 1;
+        if (out_on) {                               // q of row yo = yi-1-2R; its guide row is in ctr
+            const int yo = yi - 1 - 2 * R;
+            float q[4];
+            if (!GEN) {
+                const float n2 = c.inv_k * c.inv_k;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q[j] = fmaf(c.sA[j] * n2, c.ctr[j], c.sB[j] * n2);
+            } else {
+                const float inv_ny = c.trunc ? gf_inv_count(yo, c.height, R, c.border) : c.inv_k;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float norm = c.inv_nx[j] * inv_ny;
+                    q[j] = fmaf(c.sA[j] * norm, c.ctr[j], c.sB[j] * norm);
+                }
+            }
+            float* pq = c.gQ + (int64_t)(yo - c.out_y0) * c.ds;
+            if (c.out_lane) {
+                if (!GEN || c.vec_ok) {
+                    *reinterpret_cast<float4*>(pq) = make_float4(q[0], q[1], q[2], q[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c.x0 + j >= 0 && c.x0 + j < c.width) pq[j] = q[j];
+                }
+            }
+        }
+    }
+    if (GEN && t == steps) return;
+
+    // ================= phase B: stage 1 of row yi =================
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        c.cI[j] += c.nI[j]; c.cP[j] += c.nP[j];
+        c.cIP[j] = fmaf(c.nI[j], c.nP[j], c.cIP[j]);
+        c.cII[j] = fmaf(c.nI[j], c.nI[j], c.cII[j]);
+    }
+    if (sub_on) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            c.cI[j] -= c.oI[j]; c.cP[j] -= c.oP[j];
+            c.cIP[j] = fmaf(-c.oI[j], c.oP[j], c.cIP[j]);
+            c.cII[j] = fmaf(-c.oI[j], c.oI[j], c.cII[j]);
+        }
+    }
+    // loads of the next iteration, consumed a full iteration later
+    if (!GEN) {
+        const int64_t rn = (int64_t)(yi + 1 - c.buf_y0);
+        gf_wp_ldv(c.gI + rn * c.gs, c.nI);
+        gf_wp_ldv(c.gP + rn * c.ss, c.nP);
+        if (PH >= 2 || t + 1 >= KW) {
+            gf_wp_ldv(c.gI + (rn - KW) * c.gs, c.oI);
+            gf_wp_ldv(c.gP + (rn - KW) * c.ss, c.oP);
+        }
+        if (PH == 3) gf_wp_ldv(c.gI + (rn - 1 - 2 * R) * c.gs, c.ctr);
+        if (GF_WP_PREFETCH > 0) {   // pull the rows a few iterations ahead into L2 (clamped to the band's last row)
+            const int64_t rp = (int64_t)(min(yi + 1 + GF_WP_PREFETCH, c.yo1 + 2 * R - 1) - c.buf_y0);
+            gf_prefetch_l2(c.gI + rp * c.gs);
+            gf_prefetch_l2(c.gP + rp * c.ss);
+        }
+    } else {
+        const int sy = gf_map(yi + 1, c.height, c.border);
+        gf_wp_ld(c, c.gI, c.gs, sy < 0 ? -1 : sy - c.buf_y0, c.nI);
+        gf_wp_ld(c, c.gP, c.ss, sy < 0 ? -1 : sy - c.buf_y0, c.nP);
+        if (t + 1 >= KW) {
+            const int so = gf_map(yi + 1 - KW, c.height, c.border);
+            gf_wp_ld(c, c.gI, c.gs, so < 0 ? -1 : so - c.buf_y0, c.oI);
+            gf_wp_ld(c, c.gP, c.ss, so < 0 ? -1 : so - c.buf_y0, c.oP);
+        }
+        if (t >= 4 * R) gf_wp_ld(c, c.gI, c.gs, yi - 2 * R - c.buf_y0, c.ctr);
+    }
+    if (s1_on) {
+        // horizontal -> a, b of row yc = yi - R
+        float hI[4], hP[4], hIP[4], hII[4];
+        gf_window<R>(c.cI, hI, lane);
+        gf_window<R>(c.cP, hP, lane);
+        gf_window<R>(c.cIP, hIP, lane);
+        gf_window<R>(c.cII, hII, lane);
+        if (!GEN) {
+            // interior: every window is full, N = (2R+1)^2.  a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2)
+            const float N = (float)(KW * KW), n = c.inv_k * c.inv_k, epsN2 = c.eps * N * N;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float num = fmaf(hIP[j], N, -(hI[j] * hP[j]));
+                const float den = fmaf(hII[j], N, fmaf(-hI[j], hI[j], epsN2));
+                const float aa = num * gf_rcp(den);
+                c.va[j] = aa;
+                c.vb[j] = fmaf(-aa, hI[j], hP[j]) * n;
+            }
+        } else {
+            const int yc = yi - R;
+            const bool y_in = !c.trunc || (yc >= 0 && yc < c.height);
+            const float inv_ny = c.trunc ? gf_inv_count(yc, c.height, R, c.border) : c.inv_k;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float norm = c.inv_nx[j] * inv_ny;
+                const float mi = hI[j] * norm, mp = hP[j] * norm;
+                const float var = fmaf(-mi, mi, hII[j] * norm);
+                const float cov = fmaf(-mi, mp, hIP[j] * norm);
+                const float aa = cov * gf_rcp(var + c.eps);
+                const bool ok = c.s1_lane && y_in && c.x_in[j];
+                c.va[j] = ok ? aa : 0.f;
+                c.vb[j] = ok ? fmaf(-aa, mi, mp) : 0.f;
+            }
+            if (c.has_ab && c.out_lane && yc >= c.yo0 && yc < c.yo1) {
+                float* pa = c.gA + (int64_t)(yc - c.out_y0) * c.abs_;
+                float* pb = c.gB + (int64_t)(yc - c.out_y0) * c.abs_;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c.x0 + j < c.width) { pa[j] = c.va[j]; pb[j] = c.vb[j]; }
+            }
+        }
+    }
+}
+
+// MINB = resident CTAs per SM the register allocation is sized for: 3 (165 registers, no spills)
+// is faster when the job is one wave of short bands (4K frame); 4 (128 registers) wins when
+// there is work for many waves (8K, batches, strips of a gigapixel image).
+template <int R, int MINB>
+__global__ void __launch_bounds__(128, MINB) gf_wp_gray_kernel(const GfWpArgs a)
+{
+    using W = GfWpGeom<R>;
+    constexpr int H1 = W::H1, KW = W::KW, RC = W::RING_CELLS;
+    GF_DYN_SMEM(float, smem);
+    const int warp = threadIdx.x >> 5;
+    // work item of this warp: (strip, band, frame)
+    const long item = (long)blockIdx.x * 4 + warp;
+    const long per_frame = (long)a.nstrips * a.nbands;
+    if (item >= per_frame * a.count) return;
+    const int64_t f = item / per_frame;
+    const int band = (int)((item % per_frame) / a.nstrips), strip = (int)(item % a.nstrips);
+
+    GfWpCtx<R> c;
+    c.lane = threadIdx.x & 31;
+    c.x0 = strip * W::WOUT - 8 * H1 + 4 * c.lane;
+    c.gI = a.guide + f * a.gfs + c.x0; c.gP = a.src + f * a.sfs + c.x0; c.gQ = a.dst + f * a.dfs + c.x0;
+    c.has_ab = a.A != nullptr;
+    c.gA = c.has_ab ? a.A + f * a.abfs + c.x0 : nullptr;
+    c.gB = c.has_ab ? a.B + f * a.abfs + c.x0 : nullptr;
+    c.gs = a.gs; c.ss = a.ss; c.ds = a.ds; c.abs_ = a.abs_;
+    c.out_lane = c.lane >= 2 * H1 && c.lane < 32 - 2 * H1 && c.x0 < a.width;
+    c.s1_lane = c.lane >= H1 && c.lane < 32 - H1;
+    {
+        const bool ring_lane = c.lane >= 2 * H1 && c.lane < 32 - 2 * H1;
+        float4* base = reinterpret_cast<float4*>(smem) + (size_t)warp * (W::ring_bytes_per_warp / 16);
+        c.ring = base + (ring_lane ? c.lane - 2 * H1 : W::VL);
+        for (int s = 0; s < KW * 2; ++s) c.ring[(size_t)s * RC] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    c.width = a.width; c.height = a.height; c.border = a.border; c.buf_y0 = a.buf_y0; c.out_y0 = a.out_y0;
+    c.vec_ok = c.x0 >= 0 && c.x0 + 3 < a.width;
+    c.yo0 = a.out_y0 + band * a.hb;
+    c.yo1 = min(a.out_y0 + a.out_rows, c.yo0 + a.hb);
+    c.trunc = a.border == GF_TRUNCATE;
+    c.eps = a.eps;
+    c.inv_k = 1.0f / (float)KW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        c.inv_nx[j] = c.trunc ? gf_inv_count(c.x0 + j, a.width, R, a.border) : c.inv_k;
+        c.x_in[j] = !c.trunc || (c.x0 + j >= 0 && c.x0 + j < a.width);
+        c.sx[j] = gf_map(c.x0 + j, a.width, a.border);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        c.cI[j] = c.cP[j] = c.cIP[j] = c.cII[j] = c.sA[j] = c.sB[j] = c.va[j] = c.vb[j] = c.oI[j] = c.oP[j] = c.ctr[j] = 0.f;
+    c.slot = 0;
+    __syncwarp();
+
+    const int steps = (c.yo1 - c.yo0) + 4 * R;
+    {   // row of iteration 0
+        const int sy = gf_map(c.yo0 - 2 * R, a.height, a.border);
+        gf_wp_ld(c, c.gI, c.gs, sy < 0 ? -1 : sy - a.buf_y0, c.nI);
+        gf_wp_ld(c, c.gP, c.ss, sy < 0 ? -1 : sy - a.buf_y0, c.nP);
+    }
+    // interior warp: its 128 columns and all rows [yo0-2R, yo1+2R) lie inside the image
+    const int xl = strip * W::WOUT - 8 * H1;
+    const bool interior = xl >= 0 && xl + 128 <= a.width && c.yo0 - 2 * R >= 0 && c.yo1 + 2 * R <= a.height &&
+                          !c.has_ab && steps > 4 * R + 1;
+    int t = 0;
+    if (interior) {
+        for (; t < 2 * R; ++t) gf_wp_iter<0>(c, t, steps);
+        gf_wp_iter<5>(c, t, steps); ++t;                 // t = 2R: first stage 1, nothing to subtract yet
+        for (; t < 4 * R; ++t) gf_wp_iter<2>(c, t, steps);
+        gf_wp_iter<5>(c, t, steps); ++t;                 // t = 4R: first centre-row prefetch
+        for (; t < steps; ++t) gf_wp_iter<3>(c, t, steps);
+        gf_wp_iter<5>(c, t, steps);                      // t = steps: last output row
+    } else {
+        for (; t <= steps; ++t) gf_wp_iter<5>(c, t, steps);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+template <int R>
+static const char* gf_wp_launch(const Job& j)
+{
+    using W = GfWpGeom<R>;
+    int sms = 148, mj = 0, mn = 0;
+    gf_rt_device_info(&sms, &mj, &mn);
+    GfWpArgs a;
+    a.guide = j.guide.ptr; a.src = j.src.ptr; a.dst = const_cast<float*>(j.dst.ptr);
+    a.A = const_cast<float*>(j.A.ptr); a.B = const_cast<float*>(j.B.ptr);
+    a.gs = j.guide.stride; a.ss = j.src.stride; a.ds = j.dst.stride; a.abs_ = j.A.stride;
+    a.gfs = j.guide.frame_stride; a.sfs = j.src.frame_stride; a.dfs = j.dst.frame_stride; a.abfs = j.A.frame_stride;
+    a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.out_y0 = j.out_y0; a.out_rows = j.out_rows;
+    a.border = j.border; a.eps = j.eps; a.count = j.count;
+    a.nstrips = (j.width + W::WOUT - 1) / W::WOUT;
+    const size_t smem = 4 * W::ring_bytes_per_warp;
+    // one wave of 3 CTAs/SM when the job is small; the 4-CTA build when it spans several waves
+    const long min_items = (long)a.nstrips * ((j.out_rows + 255) / 256) * j.count;
+    bool big = min_items > (long)sms * 12;
+    if (const char* e = getenv("GF_WP_BIG")) big = atoi(e) != 0;
+    int warps_target = sms * (big ? 16 : 12);
+    if (const char* e = getenv("GF_WP_WARPS_PER_SM")) warps_target = sms * atoi(e);
+    // Bands: as many as fit in ONE wave of resident warps (a partial second wave costs more than
+    // its share), but never so short that the 4R warm-up rows dominate; large jobs get many
+    // waves of hb_max-row bands instead.
+    int nb = warps_target / (a.nstrips * j.count);
+    if (nb < 1) nb = 1;
+    int hb = (j.out_rows + nb - 1) / nb;
+    int hb_min = 4 * R, hb_max = 256;
+    if (const char* e = getenv("GF_WP_HB_MIN")) hb_min = atoi(e);
+    if (hb < hb_min) hb = hb_min;
+    if (hb > hb_max) hb = hb_max;
+    if (hb > j.out_rows) hb = j.out_rows;
+    a.hb = hb;
+    a.nbands = (j.out_rows + hb - 1) / hb;
+    const long items = (long)a.nstrips * a.nbands * j.count;
+    dim3 grid((unsigned)((items + 3) / 4)), block(128);
+    if (big) {
+        auto k = gf_wp_gray_kernel<R, 4>;
+        if (const char* e = gf_rt_set_smem(k, smem)) return e;
+        GF_LAUNCH(k, grid, block, smem, j.stream, a);
+    } else {
+        auto k = gf_wp_gray_kernel<R, 3>;
+        if (const char* e = gf_rt_set_smem(k, smem)) return e;
+        GF_LAUNCH(k, grid, block, smem, j.stream, a);
+    }
+    return gf_rt_launch_error();
+}
+
+static const char* gf_wp_try(const Job& j, bool* done, const char** name)
+{
+    *done = false;
+    if (j.color || j.r < 1 || j.r > 8) return nullptr;
+    if (getenv("GF_DISABLE_WP") || getenv("GF_DISABLE_FAST")) return nullptr;
+    const Plane* pl[3] = {&j.guide, &j.src, &j.dst};
+    for (int i = 0; i < 3; ++i)
+        if (pl[i]->channels != 1 || pl[i]->coff != 0 || (pl[i]->stride & 3) || (pl[i]->frame_stride & 3) ||
+            ((uintptr_t)pl[i]->ptr & 15))
+            return nullptr;
+    if (j.A.ptr && (j.A.channels != 1 || j.A.coff != 0)) return nullptr;
+    *done = true;
+    switch (j.r) {
+    case 1: *name = "wp_r1"; return gf_wp_launch<1>(j);
+    case 2: *name = "wp_r2"; return gf_wp_launch<2>(j);
+    case 3: *name = "wp_r3"; return gf_wp_launch<3>(j);
+    case 4: *name = "wp_r4"; return gf_wp_launch<4>(j);
+    case 5: *name = "wp_r5"; return gf_wp_launch<5>(j);
+    case 6: *name = "wp_r6"; return gf_wp_launch<6>(j);
+    case 7: *name = "wp_r7"; return gf_wp_launch<7>(j);
+    default: *name = "wp_r8"; return gf_wp_launch<8>(j);
+    }
+}
