@@ -1,0 +1,107 @@
+"""Multi-GPU partitioning of the guided filter (one process per GPU, torch.distributed).
+
+The reference is single-GPU; the path shards in two ways:
+
+* image batches (BASELINE config 3): frames are independent -> contiguous blocks of frames
+  per rank, NO collective (`shard_frames`, `filter_frames`);
+* one huge image (BASELINE config 5): row strips, rank g owns rows [g*H/G, (g+1)*H/G).  The
+  fused single-pass kernel needs 2r rows of I and p beyond each seam, so neighbours exchange
+  2r rows once per image with point-to-point send/recv (NCCL over NVLink on GPUs; gloo in the
+  CPU tests) and every rank then runs `gf_guided_gray_strip` on its halo-extended buffer.
+  The image's real top/bottom use the border rule inside the kernel.
+
+Nothing here computes pixels: it only moves halos and calls the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_frames(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block of frames for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n_frames, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def strip_rows(height: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows [y0, y1) of the image owned by `rank`."""
+    return height * rank // world, height * (rank + 1) // world
+
+
+def halo_rows(height: int, rank: int, world: int, r: int) -> Tuple[int, int]:
+    """How many rows rank needs from the rank above / below (0 at the image's real border)."""
+    y0, y1 = strip_rows(height, rank, world)
+    top = 0 if rank == 0 else min(2 * r, y0)
+    bot = 0 if rank == world - 1 else min(2 * r, height - y1)
+    return top, bot
+
+
+def alloc_strip(height: int, width: int, rank: int, world: int, r: int, device, dtype=torch.float32):
+    """Buffer for a strip WITH room for its halos, and the view of the rows the rank owns.
+    Filling the view and calling `exchange_halos_inplace` avoids any extra copy."""
+    y0, y1 = strip_rows(height, rank, world)
+    top, bot = halo_rows(height, rank, world, r)
+    buf = torch.empty((top + (y1 - y0) + bot, width), device=device, dtype=dtype)
+    return buf, buf[top:top + (y1 - y0)]
+
+
+def exchange_halos_inplace(bufs, height: int, rank: int, world: int, r: int, group=None) -> int:
+    """Fills the halo rows of every buffer in `bufs` (made by alloc_strip) from the neighbours.
+    One batched round of isend/irecv (ncclSend/ncclRecv inside a group on GPUs).  Returns the
+    global row index of row 0 of the buffers."""
+    y0, y1 = strip_rows(height, rank, world)
+    top, bot = halo_rows(height, rank, world, r)
+    own = y1 - y0
+    ops = []
+    for b in bufs:
+        if rank > 0:
+            n_up = halo_rows(height, rank - 1, world, r)[1]        # rows the upper neighbour wants
+            if n_up > own:
+                raise ValueError(f"strip of {own} rows is shorter than the {n_up}-row halo its neighbour needs")
+            ops.append(dist.P2POp(dist.isend, b[top:top + n_up], rank - 1, group))
+            ops.append(dist.P2POp(dist.irecv, b[0:top], rank - 1, group))
+        if rank < world - 1:
+            n_dn = halo_rows(height, rank + 1, world, r)[0]
+            if n_dn > own:
+                raise ValueError(f"strip of {own} rows is shorter than the {n_dn}-row halo its neighbour needs")
+            ops.append(dist.P2POp(dist.isend, b[top + own - n_dn:top + own], rank + 1, group))
+            ops.append(dist.P2POp(dist.irecv, b[top + own:top + own + bot], rank + 1, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return y0 - top
+
+
+def exchange_halos(strip: torch.Tensor, height: int, rank: int, world: int, r: int, group=None):
+    """Convenience form: takes the rank's own rows, returns (halo-extended buffer, buf_y0)."""
+    buf, view = alloc_strip(height, strip.shape[1], rank, world, r, strip.device, strip.dtype)
+    view.copy_(strip)
+    buf_y0 = exchange_halos_inplace([buf], height, rank, world, r, group)
+    return buf, buf_y0
+
+
+def filter_strip(api, I_buf: torch.Tensor, p_buf: torch.Tensor, q_out: torch.Tensor, height: int, rank: int,
+                 world: int, r: int, eps: float, border: int, stream: Optional[int] = None) -> None:
+    """Runs the fused kernel on this rank's strip.  I_buf/p_buf: halo-extended buffers after the
+    exchange (row 0 = global row y0 - top); q_out: the rank's own rows."""
+    y0, y1 = strip_rows(height, rank, world)
+    top, _ = halo_rows(height, rank, world, r)
+    w = I_buf.shape[1]
+    api.call("gf_guided_gray_strip", I_buf.data_ptr(), p_buf.data_ptr(), q_out.data_ptr(), w, height, y0 - top,
+             I_buf.shape[0], y0, y1 - y0, I_buf.stride(0), p_buf.stride(0), q_out.stride(0), r, eps, border,
+             ctypes.c_void_p(stream) if stream else None)
+
+
+def filter_frames(api, I: torch.Tensor, p: torch.Tensor, q: torch.Tensor, r: int, eps: float, border: int,
+                  stream: Optional[int] = None) -> None:
+    """Filters this rank's block of frames with ONE launch.  I: [n,h,w] (gray) or [n,h,w,3]
+    (colour guide); p, q: [n,h,w]."""
+    n, h, w = p.shape
+    gch = 1 if I.dim() == 3 else I.shape[3]
+    api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q.data_ptr(), n, w, h, gch, 0, 0, 0, 0, 0, 0, r, eps,
+             border, ctypes.c_void_p(stream) if stream else None)

@@ -1,0 +1,77 @@
+"""GPU multi-rank test (needs >= 2 GPUs on the box; `gpurun --gpus 2`): row strips with the 2r
+halo exchanged by NCCL send/recv, each rank running the fused kernel on its strip; and frame
+sharding of a batch.  One process per GPU."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, H, W, r, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import cudaimageprocessing_b200 as pkg
+        from cudaimageprocessing_b200 import dist as D
+        api = pkg.api()
+        rng = np.random.default_rng(5)
+        I = rng.random((H, W), dtype=np.float32)
+        p = rng.random((H, W), dtype=np.float32)
+        y0, y1 = D.strip_rows(H, rank, world)
+        bufI, viewI = D.alloc_strip(H, W, rank, world, r, "cuda")
+        bufP, viewP = D.alloc_strip(H, W, rank, world, r, "cuda")
+        viewI.copy_(torch.from_numpy(I[y0:y1])); viewP.copy_(torch.from_numpy(p[y0:y1]))
+        D.exchange_halos_inplace([bufI, bufP], H, rank, world, r)
+        q = torch.empty((y1 - y0, W), device="cuda")
+        D.filter_strip(api, bufI, bufP, q, H, rank, world, r, 1e-2, 0)
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, f"q_{rank}.npy"), q.cpu().numpy())
+        # batch sharding: 6 frames over the ranks, one launch per rank
+        n = 6
+        f0, f1 = D.shard_frames(n, rank, world)
+        frames = np.random.default_rng(9).random((n, 96, 160), dtype=np.float32)
+        Ib = torch.from_numpy(frames[f0:f1]).cuda()
+        qb = torch.empty_like(Ib)
+        D.filter_frames(api, Ib, Ib, qb, 4, 1e-2, 1)
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, f"b_{rank}.npy"), qb.cpu().numpy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_strips_and_batches_over_nccl(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    from oracle import c_oracle as C
+    from oracle import gf_oracle as O
+    world = min(torch.cuda.device_count(), 8)
+    H, W, r = 1024 * world // 2, 2048, 16
+    mp.spawn(_worker, args=(world, _free_port(), H, W, r, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(5)
+    I = rng.random((H, W), dtype=np.float32)
+    p = rng.random((H, W), dtype=np.float32)
+    q = np.concatenate([np.load(tmp_path / f"q_{k}.npy") for k in range(world)], axis=0)
+    assert np.abs(q - C.guided_gray_f64(I, p, r, 1e-2, 0, 8)).max() <= 1e-4
+    frames = np.random.default_rng(9).random((6, 96, 160), dtype=np.float32)
+    qb = np.concatenate([np.load(tmp_path / f"b_{k}.npy") for k in range(world)], axis=0)
+    for k in range(6):
+        assert np.abs(qb[k] - O.guided_filter_gray(frames[k], frames[k], 4, 1e-2, 1)).max() <= 1e-4
