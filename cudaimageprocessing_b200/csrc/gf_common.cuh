@@ -79,3 +79,36 @@ __host__ __device__ __forceinline__ float gf_inv_count(int i, int n, int r, int 
     int c = hi - lo + 1;
     return 1.0f / (float)(c < 1 ? 1 : c);
 }
+
+// Division by a pixel count as a two-term reciprocal: x/cnt = x*hi + x*lo to ~2^-45.
+// A single rounded reciprocal (x * fl(1/cnt)) biases every mean by up to 6e-8 relative in ONE
+// direction; that systematic shift was enough to flip ~150 pixels of the reference's uint8 KAT
+// (values sitting on x.5), against ~10 with an exact division (profiles/).
+struct GfNorm { float hi, lo; };
+__host__ __device__ __forceinline__ GfNorm gf_norm_make(float cnt)
+{
+    GfNorm n;
+    n.hi = 1.0f / cnt;
+    n.lo = fmaf(-cnt, n.hi, 1.0f) * n.hi;      // first Newton residual of the rounded reciprocal
+    return n;
+}
+// device-speed variant: hi from the fast reciprocal; hi + lo is just as accurate because lo is
+// the residual of whatever hi is
+__device__ __forceinline__ GfNorm gf_norm_fast(float cnt)
+{
+    GfNorm n;
+    n.hi = __fdividef(1.0f, cnt);
+    n.lo = fmaf(-cnt, n.hi, 1.0f) * n.hi;
+    return n;
+}
+__host__ __device__ __forceinline__ float gf_norm_apply(float x, const GfNorm& n) { return fmaf(x, n.hi, x * n.lo); }
+
+// number of pixels the 1-D window [i-r, i+r] covers, as an exact float
+__host__ __device__ __forceinline__ float gf_count(int i, int n, int r, int border)
+{
+    if (border != GF_TRUNCATE) return (float)(2 * r + 1);
+    int lo = i - r < 0 ? 0 : i - r;
+    int hi = i + r > n - 1 ? n - 1 : i + r;
+    int c = hi - lo + 1;
+    return (float)(c < 1 ? 1 : c);
+}

@@ -137,7 +137,7 @@ struct GfFastArgs {
     const float* guide; const float* src; float* dst; float* A; float* B;
     int64_t gs, ss, ds, abs_;            // row strides (floats)
     int64_t gfs, sfs, dfs, abfs;         // frame strides (floats)
-    int width, height, buf_y0, out_y0, out_rows, border, hb;
+    int width, height, buf_y0, buf_rows, out_y0, out_rows, border, hb;
     float eps;
     float* ring;                         // global ring scratch (RING_GLOBAL) or nullptr
 };
@@ -152,12 +152,13 @@ struct GfFastCtx {
     float4* ring;            // this thread's ring cells: ring[(slot*2+q)*NT]
     int lane, warp, x0, width, height, border, buf_y0, out_y0, yo0, yo1;
     bool vec_ok, trunc, s1_lane, out_lane, has_ab;
-    float eps, inv_k;
-    float inv_nx[4];
+    float eps;
+    GfNorm nk;               // 1 / (2R+1)^2
+    float cnt_x[4];
     bool x_in[4];
     int sx[4];
     // state
-    float cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], va[4], vb[4];
+    float cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], fA[4], fB[4], va[4], vb[4];
     float nI[4], nP[4], oI[4], oP[4], ctr[4];
     int slot;
 };
@@ -219,16 +220,27 @@ __device__ __forceinline__ void gf_fast_iter(GfFastCtx<R, NW>& c, int t, int ste
             c.sB[0] += hB[0] - ob.x; c.sB[1] += hB[1] - ob.y; c.sB[2] += hB[2] - ob.z; c.sB[3] += hB[3] - ob.w;
             *ca = make_float4(hA[0], hA[1], hA[2], hA[3]);
             *cb = make_float4(hB[0], hB[1], hB[2], hB[3]);
-            c.slot = c.slot + 1 == KW ? 0 : c.slot + 1;
+            // re-seed the running sums from pure additions every 2R+1 rows (see gf_wp.cuh)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c.fA[j] += hA[j]; c.fB[j] += hB[j]; }
+            c.slot = c.slot + 1;
+            if (c.slot == KW) {
+                c.slot = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { c.sA[j] = c.fA[j]; c.sB[j] = c.fB[j]; c.fA[j] = 0.f; c.fB[j] = 0.f; }
+            }
         }
         if (STEADY || t - 1 >= 4 * R) {            // q of row yo = yi-1-2R; its guide row is in ctr
             const int yo = yi - 1 - 2 * R;
-            const float inv_ny = (STEADY || !c.trunc) ? c.inv_k : gf_inv_count(yo, c.height, R, c.border);
             float q[4];
+            if (STEADY || !c.trunc) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float norm = c.inv_nx[j] * inv_ny;
-                q[j] = fmaf(c.sA[j] * norm, c.ctr[j], c.sB[j] * norm);
+                for (int j = 0; j < 4; ++j) q[j] = gf_norm_apply(fmaf(c.sA[j], c.ctr[j], c.sB[j]), c.nk);
+            } else {
+                const float cnt_y = gf_count(yo, c.height, R, c.border);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    q[j] = gf_norm_apply(fmaf(c.sA[j], c.ctr[j], c.sB[j]), gf_norm_fast(c.cnt_x[j] * cnt_y));
             }
             float* pq = c.gQ + (int64_t)(yo - c.out_y0) * c.ds;
             if (c.out_lane) {
@@ -286,17 +298,31 @@ __device__ __forceinline__ void gf_fast_iter(GfFastCtx<R, NW>& c, int t, int ste
         gf_window<R>(c.cIP, hIP, lane);
         gf_window<R>(c.cII, hII, lane);
         const bool y_in = STEADY || !c.trunc || (yc >= 0 && yc < c.height);
-        const float inv_ny = (STEADY || !c.trunc) ? c.inv_k : gf_inv_count(yc, c.height, R, c.border);
+        if (STEADY) {
+            // every window is full, N = (2R+1)^2 exact:
+            // a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2),  b = (S_p - a S_I) / N
+            const float N = (float)(KW * KW), epsN2 = c.eps * N * N;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float norm = c.inv_nx[j] * inv_ny;
-            const float mi = hI[j] * norm, mp = hP[j] * norm;
-            const float var = fmaf(-mi, mi, hII[j] * norm);
-            const float cov = fmaf(-mi, mp, hIP[j] * norm);
-            const float aa = cov * gf_rcp(var + c.eps);
-            const bool ok = c.s1_lane && y_in && c.x_in[j];
-            c.va[j] = ok ? aa : 0.f;
-            c.vb[j] = ok ? fmaf(-aa, mi, mp) : 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const float num = fmaf(hIP[j], N, -(hI[j] * hP[j]));
+                const float den = fmaf(hII[j], N, fmaf(-hI[j], hI[j], epsN2));
+                const float aa = num * gf_rcp(den);
+                c.va[j] = c.s1_lane ? aa : 0.f;
+                c.vb[j] = c.s1_lane ? gf_norm_apply(fmaf(-aa, hI[j], hP[j]), c.nk) : 0.f;
+            }
+        } else {
+            const float cnt_y = gf_count(yc, c.height, R, c.border);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const GfNorm norm = c.trunc ? gf_norm_fast(c.cnt_x[j] * cnt_y) : c.nk;
+                const float mi = gf_norm_apply(hI[j], norm), mp = gf_norm_apply(hP[j], norm);
+                const float var = fmaf(-mi, mi, gf_norm_apply(hII[j], norm));
+                const float cov = fmaf(-mi, mp, gf_norm_apply(hIP[j], norm));
+                const float aa = cov * gf_rcp(var + c.eps);
+                const bool ok = c.s1_lane && y_in && c.x_in[j];
+                c.va[j] = ok ? aa : 0.f;
+                c.vb[j] = ok ? fmaf(-aa, mi, mp) : 0.f;
+            }
         }
         if (c.has_ab && c.out_lane && yc >= c.yo0 && yc < c.yo1) {
             float* pa = c.gA + (int64_t)(yc - c.out_y0) * c.abs_;
@@ -353,16 +379,16 @@ __global__ void __launch_bounds__(NW * 32) gf_fast_gray_kernel(const GfFastArgs 
     c.out_lane = c.s1_lane && !(c.warp == 0 && c.lane < 2 * H1) && !(c.warp == NW - 1 && c.lane >= 32 - 2 * H1) &&
                  c.x0 < a.width;
     c.eps = a.eps;
-    c.inv_k = 1.0f / (float)KW;
+    c.nk = gf_norm_make((float)(KW * KW));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        c.inv_nx[j] = c.trunc ? gf_inv_count(c.x0 + j, a.width, R, a.border) : c.inv_k;
+        c.cnt_x[j] = gf_count(c.x0 + j, a.width, R, a.border);
         c.x_in[j] = !c.trunc || (c.x0 + j >= 0 && c.x0 + j < a.width);
         c.sx[j] = gf_map(c.x0 + j, a.width, a.border);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        c.cI[j] = c.cP[j] = c.cIP[j] = c.cII[j] = c.sA[j] = c.sB[j] = c.va[j] = c.vb[j] = c.oI[j] = c.oP[j] = c.ctr[j] = 0.f;
+        c.cI[j] = c.cP[j] = c.cIP[j] = c.cII[j] = c.sA[j] = c.sB[j] = c.fA[j] = c.fB[j] = c.va[j] = c.vb[j] = c.oI[j] = c.oP[j] = c.ctr[j] = 0.f;
     for (int s = 0; s < KW * 2; ++s) c.ring[(size_t)s * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
     c.slot = 0;
 
@@ -378,7 +404,8 @@ __global__ void __launch_bounds__(NW * 32) gf_fast_gray_kernel(const GfFastArgs 
     const bool cta_inside = xl >= 0 && xr <= a.width;
     int ts = 4 * R + 1;
     if (3 * R + 1 - (c.yo0 - 2 * R) > ts) ts = 3 * R + 1 - (c.yo0 - 2 * R);      // yi >= 3R+1
-    int te = a.height - 1 - (c.yo0 - 2 * R);                                      // yi + 1 <= H-1
+    if (a.buf_y0 + 2 * R - (c.yo0 - 2 * R) > ts) ts = a.buf_y0 + 2 * R - (c.yo0 - 2 * R);   // yi+1-KW inside the buffer
+    int te = min(a.height, a.buf_y0 + a.buf_rows) - 1 - (c.yo0 - 2 * R);          // yi + 1 <= last row present
     if (te > steps) te = steps;
     if (!cta_inside || te < ts) { ts = steps + 1; te = steps + 1; }
     int t = 0;
@@ -405,8 +432,8 @@ struct GfFastLaunch {
         a.A = const_cast<float*>(j.A.ptr); a.B = const_cast<float*>(j.B.ptr);
         a.gs = j.guide.stride; a.ss = j.src.stride; a.ds = j.dst.stride; a.abs_ = j.A.stride;
         a.gfs = j.guide.frame_stride; a.sfs = j.src.frame_stride; a.dfs = j.dst.frame_stride; a.abfs = j.A.frame_stride;
-        a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.out_y0 = j.out_y0; a.out_rows = j.out_rows;
-        a.border = j.border; a.eps = j.eps; a.ring = nullptr;
+        a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
+        a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.ring = nullptr;
         const int nstrips = (j.width + WOUT - 1) / WOUT;
         // band height: enough CTAs to fill the machine, but warm-up (4R rows per band) kept small
         const size_t smem = ring_global ? mb_bytes : mb_bytes + ring_bytes;

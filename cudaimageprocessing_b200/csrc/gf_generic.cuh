@@ -91,9 +91,10 @@ struct GfGrayModel {
         const float I = gf_ld(a.guide, f, row, x), p = gf_ld(a.src, f, row, x);
         v[0] = I; v[1] = p; v[2] = I * p; v[3] = I * I;
     }
-    __device__ static __forceinline__ void solve(const float (&s)[NQ1], float norm, float eps, float (&ab)[NQ2])
+    __device__ static __forceinline__ void solve(const float (&s)[NQ1], const GfNorm& norm, float eps, float (&ab)[NQ2])
     {
-        const float mi = s[0] * norm, mp = s[1] * norm, mip = s[2] * norm, mii = s[3] * norm;
+        const float mi = gf_norm_apply(s[0], norm), mp = gf_norm_apply(s[1], norm), mip = gf_norm_apply(s[2], norm),
+                    mii = gf_norm_apply(s[3], norm);
         const float var = fmaf(-mi, mi, mii);
         const float cov = fmaf(-mi, mp, mip);
         const float aa = cov / (var + eps);
@@ -101,10 +102,10 @@ struct GfGrayModel {
         ab[1] = fmaf(-aa, mi, mp);
     }
     __device__ static __forceinline__ float apply(const GfArgs& a, int64_t f, int row, int x,
-                                                  const float (&s)[NQ2], float norm)
+                                                  const float (&s)[NQ2], const GfNorm& norm)
     {
         const float I = gf_ld(a.guide, f, row, x);
-        return fmaf(s[0] * norm, I, s[1] * norm);      // gLinearTransform, guided_filter_d.cu:382-395
+        return gf_norm_apply(fmaf(s[0], I, s[1]), norm);      // gLinearTransform, guided_filter_d.cu:382-395
     }
 };
 
@@ -119,13 +120,16 @@ struct GfColorModel {
         v[4] = i0 * p; v[5] = i1 * p; v[6] = i2 * p;
         v[7] = i0 * i0; v[8] = i0 * i1; v[9] = i0 * i2; v[10] = i1 * i1; v[11] = i1 * i2; v[12] = i2 * i2;
     }
-    __device__ static __forceinline__ void solve(const float (&s)[NQ1], float norm, float eps, float (&ab)[NQ2])
+    __device__ static __forceinline__ void solve(const float (&s)[NQ1], const GfNorm& norm, float eps, float (&ab)[NQ2])
     {
-        const float m0 = s[0] * norm, m1 = s[1] * norm, m2 = s[2] * norm, mp = s[3] * norm;
-        const float c0 = fmaf(-m0, mp, s[4] * norm), c1 = fmaf(-m1, mp, s[5] * norm), c2 = fmaf(-m2, mp, s[6] * norm);
-        const float s00 = fmaf(-m0, m0, s[7] * norm) + eps, s01 = fmaf(-m0, m1, s[8] * norm),
-                    s02 = fmaf(-m0, m2, s[9] * norm), s11 = fmaf(-m1, m1, s[10] * norm) + eps,
-                    s12 = fmaf(-m1, m2, s[11] * norm), s22 = fmaf(-m2, m2, s[12] * norm) + eps;
+        float m[NQ1];
+#pragma unroll
+        for (int q = 0; q < NQ1; ++q) m[q] = gf_norm_apply(s[q], norm);
+        const float m0 = m[0], m1 = m[1], m2 = m[2], mp = m[3];
+        const float c0 = fmaf(-m0, mp, m[4]), c1 = fmaf(-m1, mp, m[5]), c2 = fmaf(-m2, mp, m[6]);
+        const float s00 = fmaf(-m0, m0, m[7]) + eps, s01 = fmaf(-m0, m1, m[8]),
+                    s02 = fmaf(-m0, m2, m[9]), s11 = fmaf(-m1, m1, m[10]) + eps,
+                    s12 = fmaf(-m1, m2, m[11]), s22 = fmaf(-m2, m2, m[12]) + eps;
         const float i00 = s11 * s22 - s12 * s12, i01 = s02 * s12 - s01 * s22, i02 = s01 * s12 - s02 * s11,
                     i11 = s00 * s22 - s02 * s02, i12 = s01 * s02 - s00 * s12, i22 = s00 * s11 - s01 * s01;
         const float inv = 1.0f / (s00 * i00 + s01 * i01 + s02 * i02);
@@ -136,10 +140,10 @@ struct GfColorModel {
         ab[3] = mp - (a0 * m0 + a1 * m1 + a2 * m2);
     }
     __device__ static __forceinline__ float apply(const GfArgs& a, int64_t f, int row, int x,
-                                                  const float (&s)[NQ2], float norm)
+                                                  const float (&s)[NQ2], const GfNorm& norm)
     {
         const float* g = a.guide.ptr + f * a.guide.frame_stride + (int64_t)row * a.guide.stride + (int64_t)x * 3;
-        return (s[0] * g[0] + s[1] * g[1] + s[2] * g[2] + s[3]) * norm;
+        return gf_norm_apply(s[0] * g[0] + s[1] * g[1] + s[2] * g[2] + s[3], norm);
     }
 };
 
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(1024) gf_generic_kernel(const GfArgs a)
     const int xe = xo0 - 2 * r + tid;         // extended column of this thread
     const int sx = gf_map(xe, a.width, a.border);
     const bool x_in = a.border != GF_TRUNCATE || (xe >= 0 && xe < a.width);
-    const float inv_nx = gf_inv_count(xe, a.width, r, a.border);
+    const float cnt_x = gf_count(xe, a.width, r, a.border);
     const int yo0 = a.out_y0 + blockIdx.y * a.hb;
     const int yo1 = min(a.out_y0 + a.out_rows, yo0 + a.hb);
     const bool out_col = tid >= 2 * r && tid < 2 * r + a.wc && xe < a.width;
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(1024) gf_generic_kernel(const GfArgs a)
         gf_hsum<NQ1>(cs1, h1, s_cs, s_tot1, r, tid, win);
         const bool y_in = a.border != GF_TRUNCATE || (yc >= 0 && yc < a.height);
         if (ab_lane && x_in && y_in) {
-            M::solve(h1, inv_nx * gf_inv_count(yc, a.height, r, a.border), a.eps, ab);
+            M::solve(h1, gf_norm_make(cnt_x * gf_count(yc, a.height, r, a.border)), a.eps, ab);
         } else {
 #pragma unroll
             for (int q = 0; q < NQ2; ++q) ab[q] = 0.f;   // outside the image / incomplete window
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(1024) gf_generic_kernel(const GfArgs a)
 
         if (t >= 4 * r && out_col) {
             const int yo = yi - 2 * r;
-            const float norm = inv_nx * gf_inv_count(yo, a.height, r, a.border);
+            const GfNorm norm = gf_norm_make(cnt_x * gf_count(yo, a.height, r, a.border));
             gf_st(a.dst, f, yo - a.out_y0, xe, M::apply(a, f, yo - a.buf_y0, xe, cs2, norm));
         }
     }
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(1024) gf_box_kernel(const GfArgs a)
     float* s_tot = s_cs + C * win;
     const int xe = blockIdx.x * a.wc - r + tid;
     const int sx = gf_map(xe, a.width, a.border);
-    const float inv_nx = gf_inv_count(xe, a.width, r, a.border);
+    const float cnt_x = gf_count(xe, a.width, r, a.border);
     const int yo0 = a.out_y0 + blockIdx.y * a.hb;
     const int yo1 = min(a.out_y0 + a.out_rows, yo0 + a.hb);
     const bool out_col = tid >= r && tid < r + a.wc && xe < a.width;
@@ -295,10 +299,10 @@ __global__ void __launch_bounds__(1024) gf_box_kernel(const GfArgs a)
         __syncthreads();                      // s_cs is rewritten next step (single stage: 2nd barrier)
         if (out_col) {
             const int yo = yi - r;
-            const float norm = inv_nx * gf_inv_count(yo, a.height, r, a.border);
+            const GfNorm norm = gf_norm_make(cnt_x * gf_count(yo, a.height, r, a.border));
             float* d = a.dst.ptr + f * a.dst.frame_stride + (int64_t)(yo - a.out_y0) * a.dst.stride + (int64_t)xe * C;
 #pragma unroll
-            for (int c = 0; c < C; ++c) d[c] = h[c] * norm;
+            for (int c = 0; c < C; ++c) d[c] = gf_norm_apply(h[c], norm);
         }
     }
 }

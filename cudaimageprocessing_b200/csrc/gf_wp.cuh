@@ -33,7 +33,7 @@ struct GfWpArgs {
     const float* guide; const float* src; float* dst; float* A; float* B;
     int64_t gs, ss, ds, abs_;
     int64_t gfs, sfs, dfs, abfs;
-    int width, height, buf_y0, out_y0, out_rows, border, hb;
+    int width, height, buf_y0, buf_rows, out_y0, out_rows, border, hb;
     int nstrips, nbands, count;
     float eps;
 };
@@ -45,11 +45,12 @@ struct GfWpCtx {
     float4* ring;            // this lane's ring cells: ring[(slot*2+q)*RING_CELLS]
     int lane, x0, width, height, border, buf_y0, out_y0, yo0, yo1;
     bool vec_ok, trunc, s1_lane, out_lane, has_ab;
-    float eps, inv_k;
-    float inv_nx[4];
+    float eps;
+    GfNorm nk;               // 1 / (2R+1)^2
+    float cnt_x[4];
     bool x_in[4];
     int sx[4];
-    float cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], va[4], vb[4];
+    float cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], fA[4], fB[4], va[4], vb[4];
     float nI[4], nP[4], oI[4], oP[4], ctr[4];
     int slot;
 };
@@ -105,21 +106,29 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
         c.sB[0] += hB[0] - ob.x; c.sB[1] += hB[1] - ob.y; c.sB[2] += hB[2] - ob.z; c.sB[3] += hB[3] - ob.w;
         *ca = make_float4(hA[0], hA[1], hA[2], hA[3]);
         *cb = make_float4(hB[0], hB[1], hB[2], hB[3]);
-        c.slot = c.slot + 1 == KW ? 0 : c.slot + 1;
+        // Re-seed: fA/fB add up the rows pushed since the ring last wrapped; when it wraps they
+        // ARE the sum of the last 2R+1 rows, computed by additions only, and replace the running
+        // sums.  The add/subtract drift of sA/sB is thereby limited to 2R+1 rows, whatever the
+        // band height (this term dominated the float32 error against the float64 oracle).
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c.fA[j] += hA[j]; c.fB[j] += hB[j]; }
+        c.slot = c.slot + 1;
+        if (c.slot == KW) {
+            c.slot = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c.sA[j] = c.fA[j]; c.sB[j] = c.fB[j]; c.fA[j] = 0.f; c.fB[j] = 0.f; }
+        }
         if (out_on) {                               // q of row yo = yi-1-2R; its guide row is in ctr
             const int yo = yi - 1 - 2 * R;
             float q[4];
-            if (!GEN) {
-                const float n2 = c.inv_k * c.inv_k;
+            if (!GEN || !c.trunc) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) q[j] = fmaf(c.sA[j] * n2, c.ctr[j], c.sB[j] * n2);
+                for (int j = 0; j < 4; ++j) q[j] = gf_norm_apply(fmaf(c.sA[j], c.ctr[j], c.sB[j]), c.nk);
             } else {
-                const float inv_ny = c.trunc ? gf_inv_count(yo, c.height, R, c.border) : c.inv_k;
+                const float cnt_y = gf_count(yo, c.height, R, c.border);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float norm = c.inv_nx[j] * inv_ny;
-                    q[j] = fmaf(c.sA[j] * norm, c.ctr[j], c.sB[j] * norm);
-                }
+                for (int j = 0; j < 4; ++j)
+                    q[j] = gf_norm_apply(fmaf(c.sA[j], c.ctr[j], c.sB[j]), gf_norm_fast(c.cnt_x[j] * cnt_y));
             }
             float* pq = c.gQ + (int64_t)(yo - c.out_y0) * c.ds;
             if (c.out_lane) {
@@ -185,25 +194,26 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
         gf_window<R>(c.cII, hII, lane);
         if (!GEN) {
             // interior: every window is full, N = (2R+1)^2.  a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2)
-            const float N = (float)(KW * KW), n = c.inv_k * c.inv_k, epsN2 = c.eps * N * N;
+            //           b = (S_p - a S_I) / N   (N is exact, the division is the two-term reciprocal)
+            const float N = (float)(KW * KW), epsN2 = c.eps * N * N;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float num = fmaf(hIP[j], N, -(hI[j] * hP[j]));
                 const float den = fmaf(hII[j], N, fmaf(-hI[j], hI[j], epsN2));
                 const float aa = num * gf_rcp(den);
                 c.va[j] = aa;
-                c.vb[j] = fmaf(-aa, hI[j], hP[j]) * n;
+                c.vb[j] = gf_norm_apply(fmaf(-aa, hI[j], hP[j]), c.nk);
             }
         } else {
             const int yc = yi - R;
             const bool y_in = !c.trunc || (yc >= 0 && yc < c.height);
-            const float inv_ny = c.trunc ? gf_inv_count(yc, c.height, R, c.border) : c.inv_k;
+            const float cnt_y = gf_count(yc, c.height, R, c.border);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float norm = c.inv_nx[j] * inv_ny;
-                const float mi = hI[j] * norm, mp = hP[j] * norm;
-                const float var = fmaf(-mi, mi, hII[j] * norm);
-                const float cov = fmaf(-mi, mp, hIP[j] * norm);
+                const GfNorm norm = c.trunc ? gf_norm_fast(c.cnt_x[j] * cnt_y) : c.nk;
+                const float mi = gf_norm_apply(hI[j], norm), mp = gf_norm_apply(hP[j], norm);
+                const float var = fmaf(-mi, mi, gf_norm_apply(hII[j], norm));
+                const float cov = fmaf(-mi, mp, gf_norm_apply(hIP[j], norm));
                 const float aa = cov * gf_rcp(var + c.eps);
                 const bool ok = c.s1_lane && y_in && c.x_in[j];
                 c.va[j] = ok ? aa : 0.f;
@@ -259,16 +269,16 @@ __global__ void __launch_bounds__(128, MINB) gf_wp_gray_kernel(const GfWpArgs a)
     c.yo1 = min(a.out_y0 + a.out_rows, c.yo0 + a.hb);
     c.trunc = a.border == GF_TRUNCATE;
     c.eps = a.eps;
-    c.inv_k = 1.0f / (float)KW;
+    c.nk = gf_norm_make((float)(KW * KW));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        c.inv_nx[j] = c.trunc ? gf_inv_count(c.x0 + j, a.width, R, a.border) : c.inv_k;
+        c.cnt_x[j] = gf_count(c.x0 + j, a.width, R, a.border);
         c.x_in[j] = !c.trunc || (c.x0 + j >= 0 && c.x0 + j < a.width);
         c.sx[j] = gf_map(c.x0 + j, a.width, a.border);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        c.cI[j] = c.cP[j] = c.cIP[j] = c.cII[j] = c.sA[j] = c.sB[j] = c.va[j] = c.vb[j] = c.oI[j] = c.oP[j] = c.ctr[j] = 0.f;
+        c.cI[j] = c.cP[j] = c.cIP[j] = c.cII[j] = c.sA[j] = c.sB[j] = c.fA[j] = c.fB[j] = c.va[j] = c.vb[j] = c.oI[j] = c.oP[j] = c.ctr[j] = 0.f;
     c.slot = 0;
     __syncwarp();
 
@@ -280,8 +290,10 @@ __global__ void __launch_bounds__(128, MINB) gf_wp_gray_kernel(const GfWpArgs a)
     }
     // interior warp: its 128 columns and all rows [yo0-2R, yo1+2R) lie inside the image
     const int xl = strip * W::WOUT - 8 * H1;
-    const bool interior = xl >= 0 && xl + 128 <= a.width && c.yo0 - 2 * R >= 0 && c.yo1 + 2 * R <= a.height &&
-                          !c.has_ab && steps > 4 * R + 1;
+    // (strictly: the last iteration prefetches one row beyond the band's halo, which must exist)
+    const int y_end = min(a.height, a.buf_y0 + a.buf_rows);
+    const bool interior = xl >= 0 && xl + 128 <= a.width && c.yo0 - 2 * R >= max(0, a.buf_y0) && c.yo1 + 2 * R < y_end &&
+                          !c.has_ab;
     int t = 0;
     if (interior) {
         for (; t < 2 * R; ++t) gf_wp_iter<0>(c, t, steps);
@@ -307,8 +319,8 @@ static const char* gf_wp_launch(const Job& j)
     a.A = const_cast<float*>(j.A.ptr); a.B = const_cast<float*>(j.B.ptr);
     a.gs = j.guide.stride; a.ss = j.src.stride; a.ds = j.dst.stride; a.abs_ = j.A.stride;
     a.gfs = j.guide.frame_stride; a.sfs = j.src.frame_stride; a.dfs = j.dst.frame_stride; a.abfs = j.A.frame_stride;
-    a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.out_y0 = j.out_y0; a.out_rows = j.out_rows;
-    a.border = j.border; a.eps = j.eps; a.count = j.count;
+    a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
+    a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
     a.nstrips = (j.width + W::WOUT - 1) / W::WOUT;
     const size_t smem = 4 * W::ring_bytes_per_warp;
     // one wave of 3 CTAs/SM when the job is small; the 4-CTA build when it spans several waves
