@@ -58,6 +58,35 @@ def main():
         print(json.dumps(out[-1]), flush=True)
         out.append(time_gray(3840, 2160, 8, env={"GF_DISABLE_FAST": 1}))
         print(json.dumps(out[-1]), flush=True)
+    if "borders" in cases:
+        for b in (0, 1, 2):
+            for env in ({}, {"GF_WP_WARPS_PER_SM": 8}, {"GF_WP_WARPS_PER_SM": 24, "GF_WP_BIG": 0}, {"GF_WP_WARPS_PER_SM": 36, "GF_WP_BIG": 0}):
+                o = time_gray(3840, 2160, 8, border=b, env=env)
+                o["border"] = b
+                out.append(o)
+                print(json.dumps(out[-1]), flush=True)
+    if "r16" in cases:
+        for env in ({}, {"GF_WP_LARGE": 1}, {"GF_WP_LARGE": 1, "GF_WP_BIG": 1}):
+            for (w, h, r) in [(3840, 2160, 16), (3840, 2160, 12), (7680, 4320, 16)]:
+                out.append(time_gray(w, h, r, nsets=3 if w * h > 3e7 else 6, iters=20, env=env))
+                print(json.dumps(out[-1]), flush=True)
+    if "color" in cases:
+        for (n, r) in [(8, 16), (8, 8), (32, 16)]:
+            g = torch.Generator(device="cuda").manual_seed(0)
+            I = torch.rand((n, 1080, 1920, 3), device="cuda", generator=g)
+            p = torch.rand((n, 1080, 1920), device="cuda", generator=g)
+            q = torch.empty_like(p)
+            s_ = torch.cuda.current_stream(); sp = ctypes.c_void_p(s_.cuda_stream)
+            def run():
+                api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q.data_ptr(), n, 1920, 1080, 3, 0, 0, 0, 0, 0, 0, r, 1e-2, 0, sp)
+            run(); run(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s_)
+            for _ in range(3): run()
+            e1.record(s_); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            out.append({"case": "color_batch", "frames": n, "r": r, "kernel": api.last_kernel(), "ms": ms, "gpix_s": n * 1920 * 1080 / ms / 1e6, "gbs_alg": 20.0 * n * 1920 * 1080 / ms / 1e6})
+            print(json.dumps(out[-1]), flush=True)
     if "one" in cases:
         out.append(time_gray(3840, 2160, 8, iters=6))
         print(json.dumps(out[-1]), flush=True)

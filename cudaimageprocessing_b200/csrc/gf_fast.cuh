@@ -493,17 +493,11 @@ static const char* gf_fast_try(const Job& j, bool* done, const char** name)
         *done = true;                                    \
         *name = NAME;                                    \
         return GfFastLaunch<RR, NWW>::go(j, name);
+    // r <= 16 is served by the warp-private kernel (gf_wp.cuh, 2x faster at r=16: no barrier,
+    // smaller ring); this CTA-wide kernel remains for radii whose halo no longer fits one warp.
     switch (j.r) {
-        GF_FAST_CASE(1, 4, "fast_r1")
-        GF_FAST_CASE(2, 4, "fast_r2")
-        GF_FAST_CASE(3, 4, "fast_r3")
-        GF_FAST_CASE(4, 4, "fast_r4")
-        GF_FAST_CASE(5, 4, "fast_r5")
-        GF_FAST_CASE(6, 4, "fast_r6")
-        GF_FAST_CASE(7, 4, "fast_r7")
-        GF_FAST_CASE(8, 4, "fast_r8")
-        GF_FAST_CASE(12, 4, "fast_r12")
-        GF_FAST_CASE(16, 4, "fast_r16")
+        GF_FAST_CASE(20, 4, "fast_r20")
+        GF_FAST_CASE(24, 8, "fast_r24")
         GF_FAST_CASE(32, 8, "fast_r32")
     default:
         return nullptr;

@@ -50,8 +50,8 @@ struct GfWpCtx {
     float cnt_x[4];
     bool x_in[4];
     int sx[4];
-    float cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], fA[4], fB[4], va[4], vb[4];
-    float nI[4], nP[4], oI[4], oP[4], ctr[4];
+    float cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], va[4], vb[4];
+    float nI[4], nP[4], oI[4], oP[4];   // oI doubles as the guide row of the next output (yi+1-KW == yi-2R)
     int slot;
 };
 
@@ -106,29 +106,18 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
         c.sB[0] += hB[0] - ob.x; c.sB[1] += hB[1] - ob.y; c.sB[2] += hB[2] - ob.z; c.sB[3] += hB[3] - ob.w;
         *ca = make_float4(hA[0], hA[1], hA[2], hA[3]);
         *cb = make_float4(hB[0], hB[1], hB[2], hB[3]);
-        // Re-seed: fA/fB add up the rows pushed since the ring last wrapped; when it wraps they
-        // ARE the sum of the last 2R+1 rows, computed by additions only, and replace the running
-        // sums.  The add/subtract drift of sA/sB is thereby limited to 2R+1 rows, whatever the
-        // band height (this term dominated the float32 error against the float64 oracle).
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { c.fA[j] += hA[j]; c.fB[j] += hB[j]; }
-        c.slot = c.slot + 1;
-        if (c.slot == KW) {
-            c.slot = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { c.sA[j] = c.fA[j]; c.sB[j] = c.fB[j]; c.fA[j] = 0.f; c.fB[j] = 0.f; }
-        }
-        if (out_on) {                               // q of row yo = yi-1-2R; its guide row is in ctr
+        c.slot = c.slot + 1 == KW ? 0 : c.slot + 1;
+        if (out_on) {                               // q of row yo = yi-1-2R; its guide row is oI
             const int yo = yi - 1 - 2 * R;
             float q[4];
             if (!GEN || !c.trunc) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) q[j] = gf_norm_apply(fmaf(c.sA[j], c.ctr[j], c.sB[j]), c.nk);
+                for (int j = 0; j < 4; ++j) q[j] = gf_norm_apply(fmaf(c.sA[j], c.oI[j], c.sB[j]), c.nk);
             } else {
                 const float cnt_y = gf_count(yo, c.height, R, c.border);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    q[j] = gf_norm_apply(fmaf(c.sA[j], c.ctr[j], c.sB[j]), gf_norm_fast(c.cnt_x[j] * cnt_y));
+                    q[j] = gf_norm_apply(fmaf(c.sA[j], c.oI[j], c.sB[j]), gf_norm_fast(c.cnt_x[j] * cnt_y));
             }
             float* pq = c.gQ + (int64_t)(yo - c.out_y0) * c.ds;
             if (c.out_lane) {
@@ -168,7 +157,6 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
             gf_wp_ldv(c.gI + (rn - KW) * c.gs, c.oI);
             gf_wp_ldv(c.gP + (rn - KW) * c.ss, c.oP);
         }
-        if (PH == 3) gf_wp_ldv(c.gI + (rn - 1 - 2 * R) * c.gs, c.ctr);
         if (GF_WP_PREFETCH > 0) {   // pull the rows a few iterations ahead into L2 (clamped to the band's last row)
             const int64_t rp = (int64_t)(min(yi + 1 + GF_WP_PREFETCH, c.yo1 + 2 * R - 1) - c.buf_y0);
             gf_prefetch_l2(c.gI + rp * c.gs);
@@ -183,7 +171,6 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
             gf_wp_ld(c, c.gI, c.gs, so < 0 ? -1 : so - c.buf_y0, c.oI);
             gf_wp_ld(c, c.gP, c.ss, so < 0 ? -1 : so - c.buf_y0, c.oP);
         }
-        if (t >= 4 * R) gf_wp_ld(c, c.gI, c.gs, yi - 2 * R - c.buf_y0, c.ctr);
     }
     if (s1_on) {
         // horizontal -> a, b of row yc = yi - R
@@ -278,7 +265,7 @@ __global__ void __launch_bounds__(128, MINB) gf_wp_gray_kernel(const GfWpArgs a)
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        c.cI[j] = c.cP[j] = c.cIP[j] = c.cII[j] = c.sA[j] = c.sB[j] = c.fA[j] = c.fB[j] = c.va[j] = c.vb[j] = c.oI[j] = c.oP[j] = c.ctr[j] = 0.f;
+        c.cI[j] = c.cP[j] = c.cIP[j] = c.cII[j] = c.sA[j] = c.sB[j] = c.va[j] = c.vb[j] = c.oI[j] = c.oP[j] = 0.f;
     c.slot = 0;
     __syncwarp();
 
@@ -325,8 +312,8 @@ static const char* gf_wp_launch(const Job& j)
     const size_t smem = 4 * W::ring_bytes_per_warp;
     // one wave of 3 CTAs/SM when the job is small; the 4-CTA build when it spans several waves
     const long min_items = (long)a.nstrips * ((j.out_rows + 255) / 256) * j.count;
-    bool big = min_items > (long)sms * 12;
-    if (const char* e = getenv("GF_WP_BIG")) big = atoi(e) != 0;
+    bool big = R <= 8 && min_items > (long)sms * 12;
+    if (const char* e = getenv("GF_WP_BIG")) big = R <= 8 && atoi(e) != 0;
     int warps_target = sms * (big ? 16 : 12);
     if (const char* e = getenv("GF_WP_WARPS_PER_SM")) warps_target = sms * atoi(e);
     // Bands: as many as fit in ONE wave of resident warps (a partial second wave costs more than
@@ -345,7 +332,7 @@ static const char* gf_wp_launch(const Job& j)
     const long items = (long)a.nstrips * a.nbands * j.count;
     dim3 grid((unsigned)((items + 3) / 4)), block(128);
     if (big) {
-        auto k = gf_wp_gray_kernel<R, 4>;
+        auto k = gf_wp_gray_kernel<R, (R <= 8 ? 4 : 3)>;
         if (const char* e = gf_rt_set_smem(k, smem)) return e;
         GF_LAUNCH(k, grid, block, smem, j.stream, a);
     } else {
@@ -359,7 +346,7 @@ static const char* gf_wp_launch(const Job& j)
 static const char* gf_wp_try(const Job& j, bool* done, const char** name)
 {
     *done = false;
-    if (j.color || j.r < 1 || j.r > 8) return nullptr;
+    if (j.color || j.r < 1 || j.r > 16) return nullptr;
     if (getenv("GF_DISABLE_WP") || getenv("GF_DISABLE_FAST")) return nullptr;
     const Plane* pl[3] = {&j.guide, &j.src, &j.dst};
     for (int i = 0; i < 3; ++i)
@@ -376,6 +363,14 @@ static const char* gf_wp_try(const Job& j, bool* done, const char** name)
     case 5: *name = "wp_r5"; return gf_wp_launch<5>(j);
     case 6: *name = "wp_r6"; return gf_wp_launch<6>(j);
     case 7: *name = "wp_r7"; return gf_wp_launch<7>(j);
-    default: *name = "wp_r8"; return gf_wp_launch<8>(j);
+    case 8: *name = "wp_r8"; return gf_wp_launch<8>(j);
+    case 9: *name = "wp_r9"; return gf_wp_launch<9>(j);
+    case 10: *name = "wp_r10"; return gf_wp_launch<10>(j);
+    case 11: *name = "wp_r11"; return gf_wp_launch<11>(j);
+    case 12: *name = "wp_r12"; return gf_wp_launch<12>(j);
+    case 13: *name = "wp_r13"; return gf_wp_launch<13>(j);
+    case 14: *name = "wp_r14"; return gf_wp_launch<14>(j);
+    case 15: *name = "wp_r15"; return gf_wp_launch<15>(j);
+    default: *name = "wp_r16"; return gf_wp_launch<16>(j);
     }
 }

@@ -128,7 +128,7 @@ def test_gray_fast(be, shape, r, border):
     I, p = synth_pair(*shape, seed=41, kind="structured")
     w = shape[1]
     q = be.guided_gray(I, p, r, 1e-2, border, pad=(-w) % 4)
-    assert be.api.last_kernel() == (f"wp_r{r}" if r <= 8 else f"fast_r{r}")
+    assert be.api.last_kernel() == (f"wp_r{r}" if r <= 16 else f"fast_r{r}")
     ref = O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)
     assert np.abs(q - ref).max() <= TOL
 
@@ -166,11 +166,11 @@ def test_kat_crop_u8_fast(be):
 
 
 @pytest.mark.parametrize("shape,r,border", [((24, 1452), 4, 0), ((120, 400), 8, 1), ((90, 400), 7, 2), ((70, 360), 3, 0),
-                                            ((60, 1100), 16, 0)])
+                                            ((60, 1100), 16, 0), ((90, 1500), 20, 0)])
 def test_gray_fast_steady_path(be, shape, r, border):
     """wide enough for a CTA strictly inside the image and tall enough for the straight-line
     steady-state loop (interior rows, 128-bit loads, constant normalisation) to run."""
     I, p = synth_pair(*shape, seed=51)
     q = be.guided_gray(I, p, r, 1e-2, border)
-    assert be.api.last_kernel() == (f"wp_r{r}" if r <= 8 else f"fast_r{r}")
+    assert be.api.last_kernel() == (f"wp_r{r}" if r <= 16 else f"fast_r{r}")
     assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
