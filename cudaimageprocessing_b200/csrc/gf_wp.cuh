@@ -1,13 +1,19 @@
-// gf_wp.cuh -- warp-private fused guided-filter kernel for small radii (R <= 8), gray float32.
+// gf_wp.cuh -- warp-private fused guided-filter kernel, gray float32, r <= 16 (the headline path).
 //
-// Same arithmetic as gf_fast.cuh (4 adjacent columns per thread, block prefix/suffix window
-// sums over warp shuffles, stage-2 row ring in shared memory, rows prefetched one iteration
-// ahead) but every WARP is an independent worker: it owns a 128-column window of which the
-// middle 32-4*H1 lanes (96 columns at R=8) produce output, and a band of rows.  Nothing is
-// exchanged between warps, so the kernel has no barrier at all, warps drift freely (latency
-// hiding without extra warps) and the ring is only 2*(2R+1) float4 per OUTPUT lane, which lets
-// 16 warps live on an SM.  The 25% redundant lanes are L1/L2 hits and cheap FADDs; what they buy
-// back is the barrier stall that dominated the exchange version (profiles/).
+// Same arithmetic as gf_fast.cuh (K adjacent columns per thread, block prefix/suffix window
+// sums over warp shuffles, stage-2 row ring in shared memory, rows loaded one iteration ahead)
+// but every WARP is an independent worker: it owns a 32*K-column window of which the middle
+// 32-4*H1 lanes (H1 = ceil(R/K) halo lanes per side and stage) produce output, and a band of
+// rows.  Nothing is exchanged between warps, so the kernel has no barrier at all, warps drift
+// freely and the ring is only 2*(2R+1)*K floats per OUTPUT lane.  The redundant halo lanes are
+// L1/L2 hits and cheap FADDs; what they buy back is the barrier stall that dominated the
+// exchange version (profiles/).
+//
+// K = 4: one float4 per lane and plane, 4 warps per CTA, 12-16 warps per SM.
+// K = 8: two float4 per lane and plane; halo shrinks to 1 lane per side and stage at r <= 8 (28
+//        of 32 lanes produce output instead of 24) and the window sums need 16 shuffles per 8
+//        columns instead of 2*10: ~1.7x fewer instructions per pixel, paid for with registers
+//        (1 warp per CTA, 7 warps per SM, each with twice the independent work).
 //
 // The row loop is cut into phases with compile-time stage flags so that a warp whose band and
 // columns are interior runs straight-line code: no border mapping, no predicates on t, constant
@@ -15,18 +21,103 @@
 #pragma once
 #include "gf_fast.cuh"
 
-#ifndef GF_WP_PREFETCH
-#define GF_WP_PREFETCH 0      // rows ahead for an L2 prefetch hint; measured: no gain on B200 (0 = off)
-#endif
+// ---- K-generic window sums ----------------------------------------------------------------------
+template <int R, int K>
+struct GfGeomK {
+    static constexpr int H1 = (R + K - 1) / K;         // halo lanes per side per stage
+    __host__ __device__ static constexpr int fdiv(int v) { return v >= 0 ? v / K : -((-v + K - 1) / K); }
+    __host__ __device__ static constexpr int dL(int j) { return fdiv(j - R); }
+    __host__ __device__ static constexpr int oL(int j) { return (j - R) - K * dL(j); }
+    __host__ __device__ static constexpr int dR(int j) { return fdiv(j + R); }
+    __host__ __device__ static constexpr int oR(int j) { return (j + R) - K * dR(j); }
+    static constexpr int dLmin = fdiv(0 - R);
+    static constexpr int dRmax = fdiv(K - 1 + R);
+};
 
-template <int R>
+template <int K>
+struct GfBlockK {
+    float pre[K];   // pre[o] = c0 + .. + co     (pre[K-1] = total)
+    float suf[K];   // suf[o] = co + .. + c(K-1) (suf[0]   = total)
+};
+
+template <int K>
+__device__ __forceinline__ GfBlockK<K> gf_block_k(const float (&c)[K])
+{
+    GfBlockK<K> b;
+    b.pre[0] = c[0];
+#pragma unroll
+    for (int o = 1; o < K; ++o) b.pre[o] = b.pre[o - 1] + c[o];
+    b.suf[K - 1] = c[K - 1];
+#pragma unroll
+    for (int o = K - 2; o >= 1; --o) b.suf[o] = c[o] + b.suf[o + 1];
+    b.suf[0] = b.pre[K - 1];
+    return b;
+}
+
+template <int R, int K, int D, int DEND>
+struct GfMidLoopK {   // tn[d - dLmin] = total of the block d lanes away, d in [D, DEND)
+    __device__ static __forceinline__ void run(float total, float (&tn)[40], int lane)
+    {
+        tn[D - GfGeomK<R, K>::dLmin] = (D == 0) ? total : gf_fetch<D>(total, lane);
+        GfMidLoopK<R, K, D + 1, DEND>::run(total, tn, lane);
+    }
+};
+template <int R, int K, int DEND>
+struct GfMidLoopK<R, K, DEND, DEND> {
+    __device__ static __forceinline__ void run(float, float (&)[40], int) {}
+};
+
+template <int R, int K, int J>
+struct GfWindowLoopK {
+    __device__ static __forceinline__ void run(const float (&c)[K], const GfBlockK<K>& b, const float (&tn)[40],
+                                               float (&out)[K], int lane)
+    {
+        using G = GfGeomK<R, K>;
+        constexpr int dl = G::dL(J), ol = G::oL(J), dr = G::dR(J), orr = G::oR(J);
+        if (dl == 0 && dr == 0) {          // window inside the thread's own block
+            float s = c[ol];
+#pragma unroll
+            for (int o = ol + 1; o <= orr; ++o) s += c[o];
+            out[J] = s;
+        } else {
+            const float left = (dl == 0) ? b.suf[ol] : gf_fetch<dl>(b.suf[ol], lane);
+            const float right = (dr == 0) ? b.pre[orr] : gf_fetch<dr>(b.pre[orr], lane);
+            float s = left;
+#pragma unroll
+            for (int d = dl + 1; d <= dr - 1; ++d) s += tn[d - G::dLmin];
+            out[J] = s + right;
+        }
+        GfWindowLoopK<R, K, J + 1>::run(c, b, tn, out, lane);
+    }
+};
+template <int R, int K>
+struct GfWindowLoopK<R, K, K> {
+    __device__ static __forceinline__ void run(const float (&)[K], const GfBlockK<K>&, const float (&)[40], float (&)[K], int) {}
+};
+
+// (2R+1)-window sums of the K columns of every lane; complete for lanes [H1, 32-H1).
+template <int R, int K>
+__device__ __forceinline__ void gf_window_k(const float (&c)[K], float (&out)[K], int lane)
+{
+    using G = GfGeomK<R, K>;
+    const GfBlockK<K> b = gf_block_k<K>(c);
+    float tn[40];
+    GfMidLoopK<R, K, G::dLmin + 1, (G::dRmax - 1 >= G::dLmin + 1 ? G::dRmax : G::dLmin + 1)>::run(b.pre[K - 1], tn, lane);
+    GfWindowLoopK<R, K, 0>::run(c, b, tn, out, lane);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------
+template <int R, int K>
 struct GfWpGeom {
-    static constexpr int H1 = GfFastGeom<R>::H1;
+    static constexpr int H1 = GfGeomK<R, K>::H1;
     static constexpr int VL = 32 - 4 * H1;          // lanes that produce output
-    static constexpr int WOUT = 4 * VL;             // output columns per warp
+    static constexpr int WOUT = K * VL;             // output columns per warp
+    static constexpr int WIN = 32 * K;              // columns a warp loads
     static constexpr int KW = 2 * R + 1;
+    static constexpr int V4 = K / 4;                // float4 per lane and plane
     static constexpr int RING_CELLS = VL + 1;       // + one dump cell shared by the halo lanes
-    static constexpr size_t ring_bytes_per_warp = (size_t)KW * 2 * RING_CELLS * 16;
+    static constexpr int WARPS = K == 4 ? 4 : 1;    // warps per CTA
+    static constexpr size_t ring_bytes_per_warp = (size_t)KW * 2 * V4 * RING_CELLS * 16;
 };
 
 struct GfWpArgs {
@@ -38,41 +129,48 @@ struct GfWpArgs {
     float eps;
 };
 
-template <int R>
+template <int R, int K>
 struct GfWpCtx {
     const float* gI; const float* gP; float* gQ; float* gA; float* gB;   // frame bases at column x0
     int64_t gs, ss, ds, abs_;
-    float4* ring;            // this lane's ring cells: ring[(slot*2+q)*RING_CELLS]
+    float4* ring;            // this lane's ring cells: ring[((slot*2+q)*V4 + v)*RING_CELLS]
     int lane, x0, width, height, border, buf_y0, out_y0, yo0, yo1;
     bool vec_ok, trunc, s1_lane, out_lane, has_ab;
     float eps;
     GfNorm nk;               // 1 / (2R+1)^2
-    float cnt_x[4];
-    bool x_in[4];
-    int sx[4];
-    float cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], va[4], vb[4];
-    float nI[4], nP[4], oI[4], oP[4];   // oI doubles as the guide row of the next output (yi+1-KW == yi-2R)
+    float cnt_x[K];
+    bool x_in[K];
+    int sx[K];
+    float cI[K], cP[K], cIP[K], cII[K], sA[K], sB[K], va[K], vb[K];
+    float nI[K], nP[K], oI[K], oP[K];   // oI doubles as the guide row of the next output (yi+1-KW == yi-2R)
     int slot;
 };
 
-template <int R>
-__device__ __forceinline__ void gf_wp_ld(const GfWpCtx<R>& c, const float* base, int64_t stride, int row, float (&v)[4])
+template <int K>
+__device__ __forceinline__ void gf_wp_ldv(const float* p, float (&v)[K])
 {
-    if (row < 0) { v[0] = v[1] = v[2] = v[3] = 0.f; return; }
-    const float* p = base + (int64_t)row * stride;
-    if (c.vec_ok) {
-        const float4 t = *reinterpret_cast<const float4*>(p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = c.sx[j] >= 0 ? p[c.sx[j] - c.x0] : 0.f;
+    for (int i = 0; i < K / 4; ++i) {
+        const float4 t = reinterpret_cast<const float4*>(p)[i];
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
     }
 }
 
-__device__ __forceinline__ void gf_wp_ldv(const float* p, float (&v)[4])
+template <int R, int K>
+__device__ __forceinline__ void gf_wp_ld(const GfWpCtx<R, K>& c, const float* base, int64_t stride, int row, float (&v)[K])
 {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    if (row < 0) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) v[j] = 0.f;
+        return;
+    }
+    const float* p = base + (int64_t)row * stride;
+    if (c.vec_ok) {
+        gf_wp_ldv<K>(p, v);
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) v[j] = c.sx[j] >= 0 ? p[c.sx[j] - c.x0] : 0.f;
+    }
 }
 
 // Iteration t.  PH selects which stages are compiled in:
@@ -81,11 +179,11 @@ __device__ __forceinline__ void gf_wp_ldv(const float* p, float (&v)[4])
 //   3  t in (4R, steps)    everything (steady state)
 //   5  any t               generic: run-time stage flags, border mapping, masks
 // PH 0/2/3 require an INTERIOR warp: all rows and columns it touches are inside the image.
-template <int PH, int R>
-__device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
+template <int PH, int R, int K>
+__device__ __forceinline__ void gf_wp_iter(GfWpCtx<R, K>& c, int t, int steps)
 {
-    using W = GfWpGeom<R>;
-    constexpr int KW = W::KW, RC = W::RING_CELLS;
+    using W = GfWpGeom<R, K>;
+    constexpr int KW = W::KW, RC = W::RING_CELLS, V4 = W::V4;
     constexpr bool GEN = PH == 5;
     const int yi = c.yo0 - 2 * R + t;
     const int lane = c.lane;
@@ -96,36 +194,43 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
 
     // ================= phase A: stage 2 of centre row yi-1-R =================
     if (a_on) {
-        float hA[4], hB[4];
-        gf_window<R>(c.va, hA, lane);
-        gf_window<R>(c.vb, hB, lane);
-        float4* ca = c.ring + (size_t)(c.slot * 2 + 0) * RC;
-        float4* cb = c.ring + (size_t)(c.slot * 2 + 1) * RC;
-        const float4 oa = *ca, ob = *cb;
-        c.sA[0] += hA[0] - oa.x; c.sA[1] += hA[1] - oa.y; c.sA[2] += hA[2] - oa.z; c.sA[3] += hA[3] - oa.w;
-        c.sB[0] += hB[0] - ob.x; c.sB[1] += hB[1] - ob.y; c.sB[2] += hB[2] - ob.z; c.sB[3] += hB[3] - ob.w;
-        *ca = make_float4(hA[0], hA[1], hA[2], hA[3]);
-        *cb = make_float4(hB[0], hB[1], hB[2], hB[3]);
+        float hA[K], hB[K];
+        gf_window_k<R, K>(c.va, hA, lane);
+        gf_window_k<R, K>(c.vb, hB, lane);
+#pragma unroll
+        for (int v = 0; v < V4; ++v) {
+            float4* ca = c.ring + (size_t)((c.slot * 2 + 0) * V4 + v) * RC;
+            float4* cb = c.ring + (size_t)((c.slot * 2 + 1) * V4 + v) * RC;
+            const float4 oa = *ca, ob = *cb;
+            c.sA[4 * v] += hA[4 * v] - oa.x; c.sA[4 * v + 1] += hA[4 * v + 1] - oa.y;
+            c.sA[4 * v + 2] += hA[4 * v + 2] - oa.z; c.sA[4 * v + 3] += hA[4 * v + 3] - oa.w;
+            c.sB[4 * v] += hB[4 * v] - ob.x; c.sB[4 * v + 1] += hB[4 * v + 1] - ob.y;
+            c.sB[4 * v + 2] += hB[4 * v + 2] - ob.z; c.sB[4 * v + 3] += hB[4 * v + 3] - ob.w;
+            *ca = make_float4(hA[4 * v], hA[4 * v + 1], hA[4 * v + 2], hA[4 * v + 3]);
+            *cb = make_float4(hB[4 * v], hB[4 * v + 1], hB[4 * v + 2], hB[4 * v + 3]);
+        }
         c.slot = c.slot + 1 == KW ? 0 : c.slot + 1;
         if (out_on) {                               // q of row yo = yi-1-2R; its guide row is oI
             const int yo = yi - 1 - 2 * R;
-            float q[4];
+            float q[K];
             if (!GEN || !c.trunc) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) q[j] = gf_norm_apply(fmaf(c.sA[j], c.oI[j], c.sB[j]), c.nk);
+                for (int j = 0; j < K; ++j) q[j] = gf_norm_apply(fmaf(c.sA[j], c.oI[j], c.sB[j]), c.nk);
             } else {
                 const float cnt_y = gf_count(yo, c.height, R, c.border);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < K; ++j)
                     q[j] = gf_norm_apply(fmaf(c.sA[j], c.oI[j], c.sB[j]), gf_norm_fast(c.cnt_x[j] * cnt_y));
             }
             float* pq = c.gQ + (int64_t)(yo - c.out_y0) * c.ds;
             if (c.out_lane) {
                 if (!GEN || c.vec_ok) {
-                    *reinterpret_cast<float4*>(pq) = make_float4(q[0], q[1], q[2], q[3]);
+#pragma unroll
+                    for (int v = 0; v < V4; ++v)
+                        reinterpret_cast<float4*>(pq)[v] = make_float4(q[4 * v], q[4 * v + 1], q[4 * v + 2], q[4 * v + 3]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < K; ++j)
                         if (c.x0 + j >= 0 && c.x0 + j < c.width) pq[j] = q[j];
                 }
             }
@@ -135,14 +240,14 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
 
     // ================= phase B: stage 1 of row yi =================
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < K; ++j) {
         c.cI[j] += c.nI[j]; c.cP[j] += c.nP[j];
         c.cIP[j] = fmaf(c.nI[j], c.nP[j], c.cIP[j]);
         c.cII[j] = fmaf(c.nI[j], c.nI[j], c.cII[j]);
     }
     if (sub_on) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < K; ++j) {
             c.cI[j] -= c.oI[j]; c.cP[j] -= c.oP[j];
             c.cIP[j] = fmaf(-c.oI[j], c.oP[j], c.cIP[j]);
             c.cII[j] = fmaf(-c.oI[j], c.oI[j], c.cII[j]);
@@ -151,16 +256,11 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
     // loads of the next iteration, consumed a full iteration later
     if (!GEN) {
         const int64_t rn = (int64_t)(yi + 1 - c.buf_y0);
-        gf_wp_ldv(c.gI + rn * c.gs, c.nI);
-        gf_wp_ldv(c.gP + rn * c.ss, c.nP);
+        gf_wp_ldv<K>(c.gI + rn * c.gs, c.nI);
+        gf_wp_ldv<K>(c.gP + rn * c.ss, c.nP);
         if (PH >= 2 || t + 1 >= KW) {
-            gf_wp_ldv(c.gI + (rn - KW) * c.gs, c.oI);
-            gf_wp_ldv(c.gP + (rn - KW) * c.ss, c.oP);
-        }
-        if (GF_WP_PREFETCH > 0) {   // pull the rows a few iterations ahead into L2 (clamped to the band's last row)
-            const int64_t rp = (int64_t)(min(yi + 1 + GF_WP_PREFETCH, c.yo1 + 2 * R - 1) - c.buf_y0);
-            gf_prefetch_l2(c.gI + rp * c.gs);
-            gf_prefetch_l2(c.gP + rp * c.ss);
+            gf_wp_ldv<K>(c.gI + (rn - KW) * c.gs, c.oI);
+            gf_wp_ldv<K>(c.gP + (rn - KW) * c.ss, c.oP);
         }
     } else {
         const int sy = gf_map(yi + 1, c.height, c.border);
@@ -174,17 +274,17 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
     }
     if (s1_on) {
         // horizontal -> a, b of row yc = yi - R
-        float hI[4], hP[4], hIP[4], hII[4];
-        gf_window<R>(c.cI, hI, lane);
-        gf_window<R>(c.cP, hP, lane);
-        gf_window<R>(c.cIP, hIP, lane);
-        gf_window<R>(c.cII, hII, lane);
+        float hI[K], hP[K], hIP[K], hII[K];
+        gf_window_k<R, K>(c.cI, hI, lane);
+        gf_window_k<R, K>(c.cP, hP, lane);
+        gf_window_k<R, K>(c.cIP, hIP, lane);
+        gf_window_k<R, K>(c.cII, hII, lane);
         if (!GEN) {
-            // interior: every window is full, N = (2R+1)^2.  a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2)
-            //           b = (S_p - a S_I) / N   (N is exact, the division is the two-term reciprocal)
+            // interior: every window is full, N = (2R+1)^2 exact:
+            // a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2),  b = (S_p - a S_I) / N
             const float N = (float)(KW * KW), epsN2 = c.eps * N * N;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < K; ++j) {
                 const float num = fmaf(hIP[j], N, -(hI[j] * hP[j]));
                 const float den = fmaf(hII[j], N, fmaf(-hI[j], hI[j], epsN2));
                 const float aa = num * gf_rcp(den);
@@ -196,7 +296,7 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
             const bool y_in = !c.trunc || (yc >= 0 && yc < c.height);
             const float cnt_y = gf_count(yc, c.height, R, c.border);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < K; ++j) {
                 const GfNorm norm = c.trunc ? gf_norm_fast(c.cnt_x[j] * cnt_y) : c.nk;
                 const float mi = gf_norm_apply(hI[j], norm), mp = gf_norm_apply(hP[j], norm);
                 const float var = fmaf(-mi, mi, gf_norm_apply(hII[j], norm));
@@ -210,33 +310,31 @@ __device__ __forceinline__ void gf_wp_iter(GfWpCtx<R>& c, int t, int steps)
                 float* pa = c.gA + (int64_t)(yc - c.out_y0) * c.abs_;
                 float* pb = c.gB + (int64_t)(yc - c.out_y0) * c.abs_;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < K; ++j)
                     if (c.x0 + j < c.width) { pa[j] = c.va[j]; pb[j] = c.vb[j]; }
             }
         }
     }
 }
 
-// MINB = resident CTAs per SM the register allocation is sized for: 3 (165 registers, no spills)
-// is faster when the job is one wave of short bands (4K frame); 4 (128 registers) wins when
-// there is work for many waves (8K, batches, strips of a gigapixel image).
-template <int R, int MINB>
-__global__ void __launch_bounds__(128, MINB) gf_wp_gray_kernel(const GfWpArgs a)
+// MINB = resident CTAs per SM the register allocation is sized for.
+template <int R, int K, int MINB>
+__global__ void __launch_bounds__(GfWpGeom<R, K>::WARPS * 32, MINB) gf_wp_gray_kernel(const GfWpArgs a)
 {
-    using W = GfWpGeom<R>;
-    constexpr int H1 = W::H1, KW = W::KW, RC = W::RING_CELLS;
+    using W = GfWpGeom<R, K>;
+    constexpr int H1 = W::H1, KW = W::KW, RC = W::RING_CELLS, V4 = W::V4;
     GF_DYN_SMEM(float, smem);
     const int warp = threadIdx.x >> 5;
     // work item of this warp: (strip, band, frame)
-    const long item = (long)blockIdx.x * 4 + warp;
+    const long item = (long)blockIdx.x * W::WARPS + warp;
     const long per_frame = (long)a.nstrips * a.nbands;
     if (item >= per_frame * a.count) return;
     const int64_t f = item / per_frame;
     const int band = (int)((item % per_frame) / a.nstrips), strip = (int)(item % a.nstrips);
 
-    GfWpCtx<R> c;
+    GfWpCtx<R, K> c;
     c.lane = threadIdx.x & 31;
-    c.x0 = strip * W::WOUT - 8 * H1 + 4 * c.lane;
+    c.x0 = strip * W::WOUT - 2 * H1 * K + K * c.lane;
     c.gI = a.guide + f * a.gfs + c.x0; c.gP = a.src + f * a.sfs + c.x0; c.gQ = a.dst + f * a.dfs + c.x0;
     c.has_ab = a.A != nullptr;
     c.gA = c.has_ab ? a.A + f * a.abfs + c.x0 : nullptr;
@@ -248,23 +346,23 @@ __global__ void __launch_bounds__(128, MINB) gf_wp_gray_kernel(const GfWpArgs a)
         const bool ring_lane = c.lane >= 2 * H1 && c.lane < 32 - 2 * H1;
         float4* base = reinterpret_cast<float4*>(smem) + (size_t)warp * (W::ring_bytes_per_warp / 16);
         c.ring = base + (ring_lane ? c.lane - 2 * H1 : W::VL);
-        for (int s = 0; s < KW * 2; ++s) c.ring[(size_t)s * RC] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < KW * 2 * V4; ++s) c.ring[(size_t)s * RC] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     c.width = a.width; c.height = a.height; c.border = a.border; c.buf_y0 = a.buf_y0; c.out_y0 = a.out_y0;
-    c.vec_ok = c.x0 >= 0 && c.x0 + 3 < a.width;
+    c.vec_ok = c.x0 >= 0 && c.x0 + K - 1 < a.width;
     c.yo0 = a.out_y0 + band * a.hb;
     c.yo1 = min(a.out_y0 + a.out_rows, c.yo0 + a.hb);
     c.trunc = a.border == GF_TRUNCATE;
     c.eps = a.eps;
     c.nk = gf_norm_make((float)(KW * KW));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < K; ++j) {
         c.cnt_x[j] = gf_count(c.x0 + j, a.width, R, a.border);
         c.x_in[j] = !c.trunc || (c.x0 + j >= 0 && c.x0 + j < a.width);
         c.sx[j] = gf_map(c.x0 + j, a.width, a.border);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < K; ++j)
         c.cI[j] = c.cP[j] = c.cIP[j] = c.cII[j] = c.sA[j] = c.sB[j] = c.va[j] = c.vb[j] = c.oI[j] = c.oP[j] = 0.f;
     c.slot = 0;
     __syncwarp();
@@ -275,18 +373,18 @@ __global__ void __launch_bounds__(128, MINB) gf_wp_gray_kernel(const GfWpArgs a)
         gf_wp_ld(c, c.gI, c.gs, sy < 0 ? -1 : sy - a.buf_y0, c.nI);
         gf_wp_ld(c, c.gP, c.ss, sy < 0 ? -1 : sy - a.buf_y0, c.nP);
     }
-    // interior warp: its 128 columns and all rows [yo0-2R, yo1+2R) lie inside the image
-    const int xl = strip * W::WOUT - 8 * H1;
-    // (strictly: the last iteration prefetches one row beyond the band's halo, which must exist)
+    // interior warp: its 32*K columns and all rows [yo0-2R, yo1+2R] lie inside the image and the
+    // buffer (the last iteration loads one row beyond the band's halo, which must exist)
+    const int xl = strip * W::WOUT - 2 * H1 * K;
     const int y_end = min(a.height, a.buf_y0 + a.buf_rows);
-    const bool interior = xl >= 0 && xl + 128 <= a.width && c.yo0 - 2 * R >= max(0, a.buf_y0) && c.yo1 + 2 * R < y_end &&
+    const bool interior = xl >= 0 && xl + W::WIN <= a.width && c.yo0 - 2 * R >= max(0, a.buf_y0) && c.yo1 + 2 * R < y_end &&
                           !c.has_ab;
     int t = 0;
     if (interior) {
         for (; t < 2 * R; ++t) gf_wp_iter<0>(c, t, steps);
         gf_wp_iter<5>(c, t, steps); ++t;                 // t = 2R: first stage 1, nothing to subtract yet
         for (; t < 4 * R; ++t) gf_wp_iter<2>(c, t, steps);
-        gf_wp_iter<5>(c, t, steps); ++t;                 // t = 4R: first centre-row prefetch
+        gf_wp_iter<5>(c, t, steps); ++t;                 // t = 4R: stage 2 still without output
         for (; t < steps; ++t) gf_wp_iter<3>(c, t, steps);
         gf_wp_iter<5>(c, t, steps);                      // t = steps: last output row
     } else {
@@ -295,10 +393,11 @@ __global__ void __launch_bounds__(128, MINB) gf_wp_gray_kernel(const GfWpArgs a)
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-template <int R>
+template <int R, int K>
 static const char* gf_wp_launch(const Job& j)
 {
-    using W = GfWpGeom<R>;
+    using W = GfWpGeom<R, K>;
+    static_assert(W::VL >= 4, "no output lanes left");
     int sms = 148, mj = 0, mn = 0;
     gf_rt_device_info(&sms, &mj, &mn);
     GfWpArgs a;
@@ -309,12 +408,17 @@ static const char* gf_wp_launch(const Job& j)
     a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
     a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
     a.nstrips = (j.width + W::WOUT - 1) / W::WOUT;
-    const size_t smem = 4 * W::ring_bytes_per_warp;
-    // one wave of 3 CTAs/SM when the job is small; the 4-CTA build when it spans several waves
+    const size_t smem = W::WARPS * W::ring_bytes_per_warp;
+    // resident warps per SM: shared memory (ring) and registers (<= 168 per thread at 12 warps)
+    int warps_sm = (int)(gf_rt_max_smem() / (smem + 1024)) * W::WARPS;
+    const int reg_cap = K == 4 ? 12 : 8;
+    if (warps_sm > reg_cap) warps_sm = reg_cap;
+    if (warps_sm < 1) warps_sm = 1;
+    // the 128-register build of the K=4 kernel holds 16 warps: better when the job spans many waves
     const long min_items = (long)a.nstrips * ((j.out_rows + 255) / 256) * j.count;
-    bool big = R <= 8 && min_items > (long)sms * 12;
-    if (const char* e = getenv("GF_WP_BIG")) big = R <= 8 && atoi(e) != 0;
-    int warps_target = sms * (big ? 16 : 12);
+    bool big = K == 4 && R <= 8 && min_items > (long)sms * 12;
+    if (const char* e = getenv("GF_WP_BIG")) big = K == 4 && R <= 8 && atoi(e) != 0;
+    int warps_target = sms * (big ? 16 : warps_sm);
     if (const char* e = getenv("GF_WP_WARPS_PER_SM")) warps_target = sms * atoi(e);
     // Bands: as many as fit in ONE wave of resident warps (a partial second wave costs more than
     // its share), but never so short that the 4R warm-up rows dominate; large jobs get many
@@ -330,13 +434,13 @@ static const char* gf_wp_launch(const Job& j)
     a.hb = hb;
     a.nbands = (j.out_rows + hb - 1) / hb;
     const long items = (long)a.nstrips * a.nbands * j.count;
-    dim3 grid((unsigned)((items + 3) / 4)), block(128);
+    dim3 grid((unsigned)((items + W::WARPS - 1) / W::WARPS)), block(W::WARPS * 32);
     if (big) {
-        auto k = gf_wp_gray_kernel<R, (R <= 8 ? 4 : 3)>;
+        auto k = gf_wp_gray_kernel<R, K, (K == 4 && R <= 8 ? 4 : 3)>;
         if (const char* e = gf_rt_set_smem(k, smem)) return e;
         GF_LAUNCH(k, grid, block, smem, j.stream, a);
     } else {
-        auto k = gf_wp_gray_kernel<R, 3>;
+        auto k = gf_wp_gray_kernel<R, K, (K == 4 ? 3 : 7)>;
         if (const char* e = gf_rt_set_smem(k, smem)) return e;
         GF_LAUNCH(k, grid, block, smem, j.stream, a);
     }
@@ -355,22 +459,27 @@ static const char* gf_wp_try(const Job& j, bool* done, const char** name)
             return nullptr;
     if (j.A.ptr && (j.A.channels != 1 || j.A.coff != 0)) return nullptr;
     *done = true;
+    const bool k8 = getenv("GF_WP_K8") != nullptr;
     switch (j.r) {
-    case 1: *name = "wp_r1"; return gf_wp_launch<1>(j);
-    case 2: *name = "wp_r2"; return gf_wp_launch<2>(j);
-    case 3: *name = "wp_r3"; return gf_wp_launch<3>(j);
-    case 4: *name = "wp_r4"; return gf_wp_launch<4>(j);
-    case 5: *name = "wp_r5"; return gf_wp_launch<5>(j);
-    case 6: *name = "wp_r6"; return gf_wp_launch<6>(j);
-    case 7: *name = "wp_r7"; return gf_wp_launch<7>(j);
-    case 8: *name = "wp_r8"; return gf_wp_launch<8>(j);
-    case 9: *name = "wp_r9"; return gf_wp_launch<9>(j);
-    case 10: *name = "wp_r10"; return gf_wp_launch<10>(j);
-    case 11: *name = "wp_r11"; return gf_wp_launch<11>(j);
-    case 12: *name = "wp_r12"; return gf_wp_launch<12>(j);
-    case 13: *name = "wp_r13"; return gf_wp_launch<13>(j);
-    case 14: *name = "wp_r14"; return gf_wp_launch<14>(j);
-    case 15: *name = "wp_r15"; return gf_wp_launch<15>(j);
-    default: *name = "wp_r16"; return gf_wp_launch<16>(j);
+    case 1: *name = "wp_r1"; return gf_wp_launch<1, 4>(j);
+    case 2: *name = "wp_r2"; return gf_wp_launch<2, 4>(j);
+    case 3: *name = "wp_r3"; return gf_wp_launch<3, 4>(j);
+    case 4: *name = "wp_r4"; return gf_wp_launch<4, 4>(j);
+    case 5: *name = "wp_r5"; return gf_wp_launch<5, 4>(j);
+    case 6: *name = "wp_r6"; return gf_wp_launch<6, 4>(j);
+    case 7: *name = "wp_r7"; return gf_wp_launch<7, 4>(j);
+    case 8:
+        if (k8) { *name = "wp8_r8"; return gf_wp_launch<8, 8>(j); }
+        *name = "wp_r8"; return gf_wp_launch<8, 4>(j);
+    case 9: *name = "wp_r9"; return gf_wp_launch<9, 4>(j);
+    case 10: *name = "wp_r10"; return gf_wp_launch<10, 4>(j);
+    case 11: *name = "wp_r11"; return gf_wp_launch<11, 4>(j);
+    case 12: *name = "wp_r12"; return gf_wp_launch<12, 4>(j);
+    case 13: *name = "wp_r13"; return gf_wp_launch<13, 4>(j);
+    case 14: *name = "wp_r14"; return gf_wp_launch<14, 4>(j);
+    case 15: *name = "wp_r15"; return gf_wp_launch<15, 4>(j);
+    default:
+        if (k8) { *name = "wp8_r16"; return gf_wp_launch<16, 8>(j); }
+        *name = "wp_r16"; return gf_wp_launch<16, 4>(j);
     }
 }

@@ -174,3 +174,13 @@ def test_gray_fast_steady_path(be, shape, r, border):
     q = be.guided_gray(I, p, r, 1e-2, border)
     assert be.api.last_kernel() == (f"wp_r{r}" if r <= 16 else f"fast_r{r}")
     assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
+
+
+@pytest.mark.parametrize("shape,r,border", [((120, 700), 8, 0), ((40, 300), 8, 1), ((150, 600), 16, 2)])
+def test_gray_wp_k8(be, shape, r, border, monkeypatch):
+    """the 8-columns-per-lane build of the warp-private kernel (GF_WP_K8): interior and border warps."""
+    monkeypatch.setenv("GF_WP_K8", "1")
+    I, p = synth_pair(*shape, seed=61, kind="structured")
+    q = be.guided_gray(I, p, r, 1e-2, border)
+    assert be.api.last_kernel() == f"wp8_r{r}"
+    assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
