@@ -18,6 +18,7 @@
 #ifdef GF_HAVE_FAST
 #include "gf_fast.cuh"
 #include "gf_wp.cuh"
+#include "gf_s8.cuh"
 #endif
 
 namespace {
@@ -173,7 +174,8 @@ int run_job(const Job& j)
 #ifdef GF_HAVE_FAST
     {
         const char* name = nullptr;
-        const char* e = gf_wp_try(j, &done, &name);
+        const char* e = gf_s8_try(j, &done, &name);
+        if (!done) e = gf_wp_try(j, &done, &name);
         if (!done) e = gf_fast_try(j, &done, &name);
         if (done) {
             if (e) rc = fail(GF_ERR_CUDA, "%s launch: %s", name, e);

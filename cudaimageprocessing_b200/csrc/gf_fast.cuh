@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(NW * 32) gf_fast_gray_kernel(const GfFastArgs 
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+#ifndef GF_NO_HOST   // (stand-alone SASS builds of one kernel define GF_NO_HOST)
 template <int R, int NW>
 struct GfFastLaunch {
     static const char* go(const Job& j, const char** name)
@@ -504,3 +505,4 @@ static const char* gf_fast_try(const Job& j, bool* done, const char** name)
     }
 #undef GF_FAST_CASE
 }
+#endif  // GF_NO_HOST

@@ -1,0 +1,596 @@
+// gf_s8.cuh -- the headline kernel: warp-private fused guided filter, gray float32, 8 ADJACENT
+// columns per lane, 256-bit global accesses, packed f32x2 arithmetic (sm_100a).
+//
+// Design target: on B200 this filter is bound by the shuffle/shared-memory
+// pipe (MIO) and by FP32 issue long before HBM, so the kernel is built to minimise both per pixel:
+//   * a lane owns 8 adjacent columns -> one LDG.256 per plane and row, one STG.256 per output row
+//     (the coalescing minimum of 8 L1 wavefronts per kB), and the cross-lane traffic of a
+//     (2R+1)-window sum drops to 2R/8 values per pixel and quantity: for R = 8 exactly one value
+//     from the left neighbour and one from the right neighbour per pixel (16 SHFL per 8 px);
+//   * window sums use additions only (float32 error ~1e-7 relative):
+//         w_j(l) = A_j(l-m) + p_j(l+m),  A_j = x_j + .. + x_7 + [totals of the next 2m-1 lanes],
+//         p_j = x_0 + .. + x_j,           m = R/8
+//     i.e. 23 additions per 8 pixels and quantity at R = 8;
+//   * vertical running sums, the a/b algebra and the output are FADD2/FFMA2/FMUL2 on column pairs
+//     (half the issue slots of scalar code; the pairs come straight out of the 256-bit loads);
+//   * every WARP is an independent worker (32*8-column window, a band of rows): no barriers; the
+//     stage-2 row ring (2R+1 rows of sum_x a, sum_x b) is the only shared-memory traffic, laid out
+//     so that every LDS.128/STS.128 is conflict-free;
+//   * the row that leaves the vertical window is re-read from L2 2R+1 rows later and doubles as
+//     the guide row of the next output; rows are loaded one iteration ahead into registers and
+//     hinted into L2 a few rows further ahead;
+//   * the row loop is cut into phases with compile-time stage flags (straight-line steady state);
+//     the vertical border is a row-index map, the horizontal border (REFLECT/REFLECT101) is
+//     per-lane mapped loads in the first/last strip only (mirrored columns give mirrored a, b, so
+//     no other code changes).
+// TRUNCATE-border jobs, A/B outputs, unaligned planes and radii without an instantiation use the
+// older kernels (gf_wp.cuh, gf_fast.cuh, gf_generic.cuh).
+#pragma once
+#include "gf_wp.cuh"
+
+#ifndef GF_S8_NEWTON
+#define GF_S8_NEWTON 1        // one Newton step after MUFU.RCP
+#endif
+#ifndef GF_S8_RESEED2
+#define GF_S8_RESEED2 1       // re-seed the stage-2 running sums from pure additions every 2R+1 rows
+#endif
+#ifndef GF_S8_RESEED1
+#define GF_S8_RESEED1 1       // same for the four stage-1 column sums
+#endif
+#ifndef GF_S8_PF
+#define GF_S8_PF 4            // rows ahead for the L2 prefetch hint (0 = off)
+#endif
+
+// ---- packed float32x2 and 256-bit access helpers -------------------------------------------------
+#ifdef GF_CPU_EMU
+static inline float2 gf_add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline float2 gf_sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+static inline float2 gf_mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+static inline float2 gf_fma2(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
+static inline void gf_ld8(const float* p, float2 (&v)[4])
+{
+    for (int i = 0; i < 4; ++i) v[i] = make_float2(p[2 * i], p[2 * i + 1]);
+}
+static inline void gf_st8(float* p, const float2 (&v)[4])
+{
+    for (int i = 0; i < 4; ++i) { p[2 * i] = v[i].x; p[2 * i + 1] = v[i].y; }
+}
+#else
+__device__ __forceinline__ float2 gf_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 gf_sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 gf_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 gf_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ void gf_ld8(const float* p, float2 (&v)[4])
+{
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y)
+                 : "l"(p));
+}
+__device__ __forceinline__ void gf_st8(float* p, const float2 (&v)[4])
+{
+    asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 ::"f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y), "l"(p)
+                 : "memory");
+}
+#endif
+__device__ __forceinline__ float2 gf_neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 gf_dup2(float a) { return make_float2(a, a); }
+
+// ---- (2R+1)-window sums over the 8 columns of every lane ------------------------------------------
+// R a multiple of 8 (m = R/8): left term = suffix of lane l-m extended by the totals of lanes
+// l-m+1 .. l+m-1 (folded in at the SENDER: one chain of 8 additions), right term = prefix of lane
+// l+m.  Complete for lanes [m, 32-m).
+// EDGE (m = 1 only): lanes flagged `left` / `right` hold the first / last 8 columns of the image;
+// their missing neighbour is the REFLECT101 mirror image of columns the lane (and its inner
+// neighbour) already holds, so its prefix/suffix terms are formed locally, again by additions only:
+//   left :  A_j(-1)   = T(0) + (x_1 + .. + x_{8-j})            (x_8 = column 0 of lane 1 = r[0])
+//   right:  p_j(L+1)  = x_6 + x_5 + .. + x_{6-j}               (x_{-1} = column 7 of lane L-1)
+struct GfS8Edge { bool left, right; };
+
+template <int R, bool EDGE>
+__device__ __forceinline__ void gf_s8_window_m8(const float2 (&c)[4], float2 (&w)[4], const GfS8Edge eg)
+{
+    constexpr int M = R / 8;
+    static_assert(R % 8 == 0 && M >= 1 && M <= 4, "folded window sum needs R = 8, 16, 24, 32");
+    static_assert(!EDGE || M == 1, "analytic image edges are implemented for R = 8 only");
+    const unsigned full = 0xffffffffu;
+    const float x[8] = {c[0].x, c[0].y, c[1].x, c[1].y, c[2].x, c[2].y, c[3].x, c[3].y};
+    float p[8];
+    p[0] = x[0];
+#pragma unroll
+    for (int o = 1; o < 8; ++o) p[o] = p[o - 1] + x[o];
+    // totals of the following lanes: tn[d] = T(l+d)
+    float tn[2 * M];
+#pragma unroll
+    for (int d = 1; d <= 2 * M - 1; ++d) tn[d] = __shfl_down_sync(full, p[7], d);
+    float e = tn[1];
+#pragma unroll
+    for (int d = 2; d <= 2 * M - 1; ++d) e += tn[d];
+    float a[8];
+    a[7] = x[7] + e;
+#pragma unroll
+    for (int o = 6; o >= 0; --o) a[o] = x[o] + a[o + 1];
+    float l[8], r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l[j] = __shfl_up_sync(full, a[j], M);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) r[j] = __shfl_down_sync(full, p[j], M);
+    r[7] = tn[M];
+    if (EDGE) {
+        const float x7m = __shfl_up_sync(full, x[7], 1);
+        float pp[8];                                   // pp[n] = x_1 + .. + x_n
+        pp[1] = x[1];
+#pragma unroll
+        for (int n = 2; n < 8; ++n) pp[n] = pp[n - 1] + x[n];
+        float lv[8], rv[8];
+        lv[0] = (p[7] + pp[7]) + r[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) lv[j] = p[7] + pp[8 - j];
+        rv[0] = x[6];
+#pragma unroll
+        for (int j = 1; j < 7; ++j) rv[j] = rv[j - 1] + x[6 - j];
+        rv[7] = rv[6] + x7m;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            l[j] = eg.left ? lv[j] : l[j];
+            r[j] = eg.right ? rv[j] : r[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = gf_add2(make_float2(l[2 * i], l[2 * i + 1]), make_float2(r[2 * i], r[2 * i + 1]));
+}
+
+template <int R, bool EDGE>
+__device__ __forceinline__ void gf_s8_window(const float2 (&c)[4], float2 (&w)[4], int lane, const GfS8Edge eg)
+{
+    if constexpr (R % 8 == 0) {
+        gf_s8_window_m8<R, EDGE>(c, w, eg);
+    } else {
+        static_assert(!EDGE, "analytic image edges need R = 8");
+        const float x[8] = {c[0].x, c[0].y, c[1].x, c[1].y, c[2].x, c[2].y, c[3].x, c[3].y};
+        float o[8];
+        gf_window_k<R, 8>(x, o, lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = make_float2(o[2 * i], o[2 * i + 1]);
+    }
+}
+
+// ---- geometry ------------------------------------------------------------------------------------
+template <int R>
+struct GfS8Geom {
+    static constexpr int H1 = (R + 7) / 8;           // halo lanes per side per stage
+    static constexpr int VL = 32 - 4 * H1;           // lanes that produce output
+    static constexpr int WOUT = 8 * VL;              // output columns per warp
+    static constexpr int WIN = 256;                  // columns a warp loads
+    static constexpr int KW = 2 * R + 1;
+    static constexpr int SLOT_F2 = 2 * 4 * VL;       // float2 per ring row: [q][pair][cell]
+    static constexpr size_t ring_bytes = (size_t)KW * SLOT_F2 * 8;
+};
+
+template <int R>
+struct GfS8Ctx {
+    const float* gI; const float* gP; float* gQ;     // frame bases at (row buf_y0 / out_y0, this lane's first column)
+    int gs, ss, ds;                                  // row strides; (rows * stride) fits 31 bits (host check)
+    float2* ring;                                    // this lane's cell of ring row 0
+    int lane, x0, width, height, border, buf_y0, buf_ylast, out_y0, yi0;
+    bool vec_ok, ring_lane, out_lane;
+    GfS8Edge edge;                                   // MODE 1 only
+    int sx[8];                                       // XMAP only: source column of each of the 8 columns, relative to x0
+    float eps;
+    GfNorm nk;                                       // 1 / (2R+1)^2
+    float2 cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], va[4], vb[4];
+    float2 fI[4], fP[4], fIP[4], fII[4], fA[4], fB[4];   // re-seed accumulators
+    float2 nI[4], nP[4], oI[4], oP[4];               // oI doubles as the guide row of the next output
+};
+
+struct GfS8Flags { bool a_on, sub2_on, out_on, b_on, sub_on, s1_on, ld_old; };
+
+// single reflection (callers guarantee |overshoot| < n)
+__device__ __forceinline__ int gf_s8_map_y(int y, int n, int border)
+{
+    const int e = border == GF_REFLECT ? 1 : 0;
+    if (y < 0) y = -y - e;
+    if (y >= n) y = 2 * n - 2 + e - y;
+    return y;
+}
+
+__device__ __forceinline__ float gf_s8_rcp(float d)
+{
+#ifdef GF_CPU_EMU
+    return 1.0f / d;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));    // MUFU.RCP, no range fix-up: |d| is in [eps N^2, ~2 N^2]
+    return r;
+#endif
+}
+
+template <int MODE, int R>
+__device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R>& c, const float* rowp, float2 (&v)[4])
+{
+    if (MODE != 2 || c.vec_ok) {
+        gf_ld8(rowp, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = make_float2(rowp[c.sx[2 * i]], rowp[c.sx[2 * i + 1]]);
+    }
+}
+
+// c = f, f = 0: f holds exactly the rows of the current window, summed without a subtraction
+template <int R>
+__device__ __forceinline__ void gf_s8_reseed1(GfS8Ctx<R>& c)
+{
+    if (!GF_S8_RESEED1) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c.cI[i] = c.fI[i]; c.cP[i] = c.fP[i]; c.cIP[i] = c.fIP[i]; c.cII[i] = c.fII[i];
+        c.fI[i] = c.fP[i] = c.fIP[i] = c.fII[i] = make_float2(0.f, 0.f);
+    }
+}
+template <int R>
+__device__ __forceinline__ void gf_s8_reseed2(GfS8Ctx<R>& c)
+{
+    if (!GF_S8_RESEED2) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c.sA[i] = c.fA[i]; c.sB[i] = c.fB[i];
+        c.fA[i] = c.fB[i] = make_float2(0.f, 0.f);
+    }
+}
+
+// Iteration t: phase A = stage 2 (+ output) of the a, b row produced by iteration t-1 (ring row
+// `slot`), phase B = stage 1 of input row yi = yi0 + t.  PH picks the stages at compile time:
+//   0  t in [0, 2R)         vertical add only
+//   2  t in [2R+1, 4R]      stage 1 with subtraction, stage 2 without subtraction/output
+//   3  t in [4R+2, steps)   everything (steady state)
+//   9  run-time flags (the three transition iterations)
+template <int PH, int R, int MODE>
+__device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, const GfS8Flags rt)
+{
+    using G = GfS8Geom<R>;
+    constexpr int KW = G::KW, VL = G::VL;
+    constexpr bool RT = PH == 9, XMAP = MODE == 2, EDGE = MODE == 1;
+    const bool a_on = RT ? rt.a_on : PH >= 2;
+    const bool sub2_on = RT ? rt.sub2_on : PH >= 3;
+    const bool out_on = RT ? rt.out_on : PH >= 3;
+    const bool b_on = RT ? rt.b_on : true;
+    const bool sub_on = RT ? rt.sub_on : PH >= 2;
+    const bool s1_on = RT ? rt.s1_on : PH >= 2;
+    const bool ld_old = RT ? rt.ld_old : PH >= 2;
+    const bool acc1 = GF_S8_RESEED1 && (RT ? rt.sub_on : PH >= 2);     // t >= 2R+1
+    const bool acc2 = GF_S8_RESEED2 && (RT ? rt.sub2_on : PH >= 3);    // t >= 4R+2
+    const int yi = c.yi0 + t;
+    const int lane = c.lane;
+
+    // ================= phase A: stage 2 of centre row yi-1-R =================
+    if (a_on) {
+        float2 hA[4], hB[4];
+        gf_s8_window<R, EDGE>(c.va, hA, lane, c.edge);
+        gf_s8_window<R, EDGE>(c.vb, hB, lane, c.edge);
+        if (c.ring_lane) {
+            float2* s = c.ring + slot * G::SLOT_F2;
+            if (sub2_on) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    c.sA[i] = gf_add2(c.sA[i], gf_sub2(hA[i], s[i * VL]));
+                    c.sB[i] = gf_add2(c.sB[i], gf_sub2(hB[i], s[(4 + i) * VL]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { c.sA[i] = gf_add2(c.sA[i], hA[i]); c.sB[i] = gf_add2(c.sB[i], hB[i]); }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { s[i * VL] = hA[i]; s[(4 + i) * VL] = hB[i]; }
+        }
+        if (acc2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { c.fA[i] = gf_add2(c.fA[i], hA[i]); c.fB[i] = gf_add2(c.fB[i], hB[i]); }
+        }
+        if (out_on) {                                   // q of row yo = yi-1-2R; its guide row is oI
+            const int yo = yi - 1 - 2 * R;
+            float2 q[4];
+            const float2 nh = gf_dup2(c.nk.hi), nl = gf_dup2(c.nk.lo);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 v = gf_fma2(c.sA[i], c.oI[i], c.sB[i]);
+                q[i] = gf_fma2(v, nh, gf_mul2(v, nl));
+            }
+            float* pq = c.gQ + (yo - c.out_y0) * c.ds;
+            if (c.out_lane) {
+                if (!XMAP || c.vec_ok) {
+                    gf_st8(pq, q);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (c.x0 + 2 * i >= 0 && c.x0 + 2 * i < c.width) pq[2 * i] = q[i].x;
+                        if (c.x0 + 2 * i + 1 >= 0 && c.x0 + 2 * i + 1 < c.width) pq[2 * i + 1] = q[i].y;
+                    }
+                }
+            }
+        }
+    }
+    if (!b_on) return;
+
+    // ================= phase B: stage 1 of row yi =================
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (sub_on) {
+            c.cI[i] = gf_add2(c.cI[i], gf_sub2(c.nI[i], c.oI[i]));
+            c.cP[i] = gf_add2(c.cP[i], gf_sub2(c.nP[i], c.oP[i]));
+            c.cIP[i] = gf_fma2(gf_neg2(c.oI[i]), c.oP[i], gf_fma2(c.nI[i], c.nP[i], c.cIP[i]));
+            c.cII[i] = gf_fma2(gf_neg2(c.oI[i]), c.oI[i], gf_fma2(c.nI[i], c.nI[i], c.cII[i]));
+        } else {
+            c.cI[i] = gf_add2(c.cI[i], c.nI[i]);
+            c.cP[i] = gf_add2(c.cP[i], c.nP[i]);
+            c.cIP[i] = gf_fma2(c.nI[i], c.nP[i], c.cIP[i]);
+            c.cII[i] = gf_fma2(c.nI[i], c.nI[i], c.cII[i]);
+        }
+        if (acc1) {
+            c.fI[i] = gf_add2(c.fI[i], c.nI[i]);
+            c.fP[i] = gf_add2(c.fP[i], c.nP[i]);
+            c.fIP[i] = gf_fma2(c.nI[i], c.nP[i], c.fIP[i]);
+            c.fII[i] = gf_fma2(c.nI[i], c.nI[i], c.fII[i]);
+        }
+    }
+    // rows of the next iteration, consumed a full iteration later
+    {
+        int rn = gf_s8_map_y(yi + 1, c.height, c.border);
+        rn = rn > c.buf_ylast ? c.buf_ylast : rn;
+        const int on = rn - c.buf_y0;
+        gf_s8_ld<MODE>(c, c.gI + on * c.gs, c.nI);
+        gf_s8_ld<MODE>(c, c.gP + on * c.ss, c.nP);
+        if (ld_old) {
+            const int oo = gf_s8_map_y(yi + 1 - KW, c.height, c.border) - c.buf_y0;
+            gf_s8_ld<MODE>(c, c.gI + oo * c.gs, c.oI);
+            gf_s8_ld<MODE>(c, c.gP + oo * c.ss, c.oP);
+        }
+        if (GF_S8_PF > 0 && !XMAP && lane < 8) {
+            const int rp = yi + 1 + GF_S8_PF;
+            if (rp <= c.buf_ylast) {
+                const int op = rp - c.buf_y0;
+                gf_prefetch_l2(c.gI + op * c.gs + 24 * lane);      // 8 lines of 128 B = this warp's 256 columns
+                gf_prefetch_l2(c.gP + op * c.ss + 24 * lane);
+            }
+        }
+    }
+    if (s1_on) {
+        // horizontal -> a, b of row yi - R.  Every window is full (REFLECT borders mirror the data):
+        //   a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2),   b = (S_p - a S_I) / N
+        float2 hI[4], hP[4], hIP[4], hII[4];
+        gf_s8_window<R, EDGE>(c.cI, hI, lane, c.edge);
+        gf_s8_window<R, EDGE>(c.cP, hP, lane, c.edge);
+        gf_s8_window<R, EDGE>(c.cIP, hIP, lane, c.edge);
+        gf_s8_window<R, EDGE>(c.cII, hII, lane, c.edge);
+        const float N = (float)(KW * KW);
+        const float2 mN = gf_dup2(-N), mE = gf_dup2(-c.eps * N * N);
+        const float2 nh = gf_dup2(c.nk.hi), nl = gf_dup2(c.nk.lo);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 nnum = gf_fma2(hI[i], hP[i], gf_mul2(hIP[i], mN));           // -(numerator)
+            const float2 nden = gf_fma2(hI[i], hI[i], gf_fma2(hII[i], mN, mE));       // -(denominator) < 0
+            float2 rc = make_float2(gf_s8_rcp(nden.x), gf_s8_rcp(nden.y));
+            if (GF_S8_NEWTON) {
+                const float2 e = gf_fma2(gf_neg2(nden), rc, gf_dup2(1.0f));
+                rc = gf_fma2(e, rc, rc);
+            }
+            const float2 aa = gf_mul2(nnum, rc);
+            const float2 bn = gf_fma2(gf_neg2(aa), hI[i], hP[i]);                      // N * b
+            c.va[i] = aa;
+            c.vb[i] = gf_fma2(bn, nh, gf_mul2(bn, nl));
+        }
+    }
+}
+
+// Warm-up rows t in [0, 2R): vertical accumulation only.  Nothing else is going on, so a single
+// row in flight would expose the full DRAM latency 2R times; rows are loaded CH at a time instead.
+// On entry nI/nP hold row yi0 (t = 0); on exit they hold row yi0 + 2R.
+template <int R, int MODE>
+__device__ __forceinline__ void gf_s8_warmup(GfS8Ctx<R>& c)
+{
+    constexpr int CH = 4, NROWS = 2 * R;
+    float2 bI[CH][4], bP[CH][4];
+#pragma unroll 1
+    for (int t0 = 0; t0 < NROWS; t0 += CH) {
+        // rows t0+1 .. t0+CH  (row t0 is already in nI/nP)
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            int rn = gf_s8_map_y(c.yi0 + t0 + 1 + k, c.height, c.border);
+            rn = rn > c.buf_ylast ? c.buf_ylast : rn;
+            const int on = rn - c.buf_y0;
+            gf_s8_ld<MODE>(c, c.gI + on * c.gs, bI[k]);
+            gf_s8_ld<MODE>(c, c.gP + on * c.ss, bP[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            if (t0 + k < NROWS) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    c.cI[i] = gf_add2(c.cI[i], c.nI[i]);
+                    c.cP[i] = gf_add2(c.cP[i], c.nP[i]);
+                    c.cIP[i] = gf_fma2(c.nI[i], c.nP[i], c.cIP[i]);
+                    c.cII[i] = gf_fma2(c.nI[i], c.nI[i], c.cII[i]);
+                    c.nI[i] = bI[k][i]; c.nP[i] = bP[k][i];
+                }
+            }
+        }
+    }
+}
+
+// The row loop of one band.  Both re-seed points fall on iterations t = 2R (mod 2R+1), so the
+// steady state is an outer loop over periods of 2R+1 rows whose inner loop is straight-line code.
+template <int R, int MODE>
+__device__ __forceinline__ void gf_s8_band(GfS8Ctx<R>& c, int steps)
+{
+    constexpr int KW = 2 * R + 1;
+    static_assert((2 * R) % 4 == 0 || true, "");
+    GfS8Flags f;
+    int t = 0;
+    if ((2 * R) % 4 == 0) {
+        gf_s8_warmup<R, MODE>(c);
+        t = 2 * R;
+    } else {
+        f = GfS8Flags{false, false, false, true, false, false, false};
+        for (; t < 2 * R; ++t) gf_s8_iter<0, R, MODE>(c, t, 0, f);
+    }
+    f = GfS8Flags{false, false, false, true, false, true, true};          // t = 2R: first stage 1, nothing to subtract yet
+    gf_s8_iter<9, R, MODE>(c, t, 0, f); ++t;
+    for (; t <= 4 * R; ++t) gf_s8_iter<2, R, MODE>(c, t, t - (2 * R + 1), f);
+    int slot = KW - 1;
+    if (t < steps) {
+        f = GfS8Flags{true, false, true, true, true, true, true};         // t = 4R+1: first output, ring just full
+        gf_s8_iter<9, R, MODE>(c, t, slot, f); ++t;
+        gf_s8_reseed1<R>(c);
+        slot = 0;
+        while (t + KW <= steps) {
+            for (int s = 0; s < KW; ++s, ++t) gf_s8_iter<3, R, MODE>(c, t, s, f);
+            gf_s8_reseed1<R>(c);
+            gf_s8_reseed2<R>(c);
+        }
+        for (; t < steps; ++t, ++slot) gf_s8_iter<3, R, MODE>(c, t, slot, f);
+    }
+    // t = steps: last output row only
+    f = GfS8Flags{true, steps >= 4 * R + 2, true, false, false, false, false};
+    gf_s8_iter<9, R, MODE>(c, t, slot, f);
+}
+
+// Strip geometry.  edge_ok (R = 8, REFLECT101, width % 8 == 0, width >= 256): the first strip
+// starts at column 0 and the last one ends at the last column, their image-side lanes use the
+// analytic mirror (MODE 1) and all their lanes on that side produce output.  Otherwise strips
+// that overhang the image load through the per-column border map (MODE 2).
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
+{
+    using G = GfS8Geom<R>;
+    constexpr int H1 = G::H1, KW = G::KW, VL = G::VL;
+    GF_DYN_SMEM(float, smem);
+    const long item = (long)blockIdx.x;
+    const long per_frame = (long)a.nstrips * a.nbands;
+    const int64_t f = item / per_frame;
+    const int band = (int)((item % per_frame) / a.nstrips), strip = (int)(item % a.nstrips);
+    const bool edge_ok = R == 8 && a.border == GF_REFLECT101 && (a.width & 7) == 0 && a.width >= G::WIN;
+    const bool first = strip == 0, last = strip == a.nstrips - 1;
+
+    GfS8Ctx<R> c;
+    c.lane = threadIdx.x & 31;
+    int xl = strip * G::WOUT - 2 * H1 * 8, lane_lo = 2 * H1, col_min = 0;
+    int mode = 0;
+    if (edge_ok && (first || last)) {
+        mode = 1;
+        if (first) { xl = 0; lane_lo = 0; }
+        if (last && !first) { xl = a.width - G::WIN; lane_lo = 4 * H1; col_min = strip * G::WOUT; }
+    } else if (xl < 0 || xl + G::WIN > a.width) {
+        mode = 2;
+    }
+    c.x0 = xl + 8 * c.lane;
+    c.edge.left = mode == 1 && first && c.lane == 0;
+    c.edge.right = mode == 1 && last && c.x0 + 8 == a.width;
+    c.gI = a.guide + f * a.gfs + c.x0; c.gP = a.src + f * a.sfs + c.x0; c.gQ = a.dst + f * a.dfs + c.x0;
+    c.gs = (int)a.gs; c.ss = (int)a.ss; c.ds = (int)a.ds;
+    c.ring_lane = c.lane >= lane_lo && c.lane < lane_lo + VL;
+    c.out_lane = c.ring_lane && c.x0 < a.width && c.x0 >= col_min;
+    c.ring = reinterpret_cast<float2*>(smem) + (c.ring_lane ? c.lane - lane_lo : 0);
+    c.width = a.width; c.height = a.height; c.border = a.border; c.buf_y0 = a.buf_y0; c.out_y0 = a.out_y0;
+    {
+        const int yl = a.buf_y0 + a.buf_rows - 1;
+        c.buf_ylast = yl < a.height - 1 ? yl : a.height - 1;
+    }
+    c.vec_ok = c.x0 >= 0 && c.x0 + 7 < a.width;
+    const int yo0 = a.out_y0 + band * a.hb;
+    const int yo1 = min(a.out_y0 + a.out_rows, yo0 + a.hb);
+    c.yi0 = yo0 - 2 * R;
+    c.eps = a.eps;
+    c.nk = gf_norm_make((float)(KW * KW));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c.cI[i] = c.cP[i] = c.cIP[i] = c.cII[i] = c.sA[i] = c.sB[i] = c.va[i] = c.vb[i] = make_float2(0.f, 0.f);
+        c.fI[i] = c.fP[i] = c.fIP[i] = c.fII[i] = c.fA[i] = c.fB[i] = make_float2(0.f, 0.f);
+        c.oI[i] = c.oP[i] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c.sx[j] = mode == 2 ? gf_map(c.x0 + j, a.width, a.border) - c.x0 : j;
+
+    const int steps = (yo1 - yo0) + 4 * R;
+    const int o0 = gf_s8_map_y(c.yi0, a.height, a.border) - a.buf_y0;       // row of iteration 0
+    if (mode == 2) {
+        gf_s8_ld<2>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<2>(c, c.gP + o0 * c.ss, c.nP);
+        gf_s8_band<R, 2>(c, steps);
+    } else {
+        gf_s8_ld<0>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<0>(c, c.gP + o0 * c.ss, c.nP);
+        if constexpr (R == 8) {
+            if (mode == 1) { gf_s8_band<R, 1>(c, steps); return; }
+        }
+        gf_s8_band<R, 0>(c, steps);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+#ifndef GF_NO_HOST   // (stand-alone SASS builds of one kernel define GF_NO_HOST)
+template <int R>
+static const char* gf_s8_launch(const Job& j)
+{
+    using G = GfS8Geom<R>;
+    static_assert(G::VL >= 8, "too few output lanes");
+    int sms = 148, mj = 0, mn = 0;
+    gf_rt_device_info(&sms, &mj, &mn);
+    GfWpArgs a;
+    a.guide = j.guide.ptr; a.src = j.src.ptr; a.dst = const_cast<float*>(j.dst.ptr);
+    a.A = nullptr; a.B = nullptr;
+    a.gs = j.guide.stride; a.ss = j.src.stride; a.ds = j.dst.stride; a.abs_ = 0;
+    a.gfs = j.guide.frame_stride; a.sfs = j.src.frame_stride; a.dfs = j.dst.frame_stride; a.abfs = 0;
+    a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
+    a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
+    a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
+    const size_t smem = G::ring_bytes;
+    // resident warps per SM: the ring in shared memory (228 kB per SM, 1 kB reserved per CTA)
+    int warps_sm = (int)((size_t)228 * 1024 / (smem + 1024));
+    if (warps_sm > 8) warps_sm = 8;
+    if (warps_sm < 1) warps_sm = 1;
+    if (const char* e = getenv("GF_S8_WARPS_PER_SM")) warps_sm = atoi(e);
+    // Bands: ONE wave of resident warps when the job is small, hb_max-row bands otherwise
+    const long target = (long)sms * warps_sm;
+    long nb = target / ((long)a.nstrips * j.count);
+    if (nb < 1) nb = 1;
+    int hb = (int)((j.out_rows + nb - 1) / nb);
+    int hb_min = 2 * R + 8, hb_max = 512;
+    if (const char* e = getenv("GF_S8_HB_MIN")) hb_min = atoi(e);
+    if (const char* e = getenv("GF_S8_HB_MAX")) hb_max = atoi(e);
+    if (const char* e = getenv("GF_S8_HB")) hb = atoi(e);
+    if (hb < hb_min) hb = hb_min;
+    if (hb > hb_max) hb = hb_max;
+    if (hb > j.out_rows) hb = j.out_rows;
+    a.hb = hb;
+    a.nbands = (j.out_rows + hb - 1) / hb;
+    const long items = (long)a.nstrips * a.nbands * j.count;
+    dim3 grid((unsigned)items), block(32);
+    constexpr int MINB = G::ring_bytes * 7 + 7 * 1024 <= 228 * 1024 ? 7 : (G::ring_bytes * 4 + 4 * 1024 <= 228 * 1024 ? 4 : 2);
+    auto k = gf_s8_gray_kernel<R, MINB>;
+    if (const char* e = gf_rt_set_smem(k, smem)) return e;
+    GF_LAUNCH(k, grid, block, smem, j.stream, a);
+    return gf_rt_launch_error();
+}
+
+static const char* gf_s8_try(const Job& j, bool* done, const char** name)
+{
+    *done = false;
+    if (j.color || j.border == GF_TRUNCATE || j.A.ptr) return nullptr;
+    if (getenv("GF_DISABLE_S8") || getenv("GF_DISABLE_FAST")) return nullptr;
+    const Plane* pl[3] = {&j.guide, &j.src, &j.dst};
+    for (int i = 0; i < 3; ++i)
+        if (pl[i]->channels != 1 || pl[i]->coff != 0 || (pl[i]->stride & 7) || (pl[i]->frame_stride & 7) ||
+            ((uintptr_t)pl[i]->ptr & 31))
+            return nullptr;
+    // row offsets inside a frame are 32-bit in the kernel
+    if ((int64_t)j.buf_rows * j.guide.stride >= (1ll << 31) || (int64_t)j.buf_rows * j.src.stride >= (1ll << 31) ||
+        (int64_t)j.out_rows * j.dst.stride >= (1ll << 31))
+        return nullptr;
+    // single reflections only, and at least one full warp window of columns
+    if (j.height < 4 * j.r + 2 || j.width < 4 * j.r + 2 || j.width < 64) return nullptr;
+    switch (j.r) {
+    case 4: *done = true; *name = "s8_r4"; return gf_s8_launch<4>(j);
+    case 7: *done = true; *name = "s8_r7"; return gf_s8_launch<7>(j);
+    case 8: *done = true; *name = "s8_r8"; return gf_s8_launch<8>(j);
+    case 16: *done = true; *name = "s8_r16"; return gf_s8_launch<16>(j);
+    default: return nullptr;
+    }
+}
+#endif  // GF_NO_HOST

@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(GfWpGeom<R, K>::WARPS * 32, MINB) gf_wp_gray_k
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+#ifndef GF_NO_HOST   // (stand-alone SASS builds of one kernel define GF_NO_HOST)
 template <int R, int K>
 static const char* gf_wp_launch(const Job& j)
 {
@@ -483,3 +484,4 @@ static const char* gf_wp_try(const Job& j, bool* done, const char** name)
         *name = "wp_r16"; return gf_wp_launch<16, 4>(j);
     }
 }
+#endif  // GF_NO_HOST

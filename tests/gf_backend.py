@@ -120,11 +120,23 @@ class EmuBackend(_Base):
         from emu.build_emu import build_emu
         self.api = GfApi(ctypes.CDLL(build_emu()))
 
+    @staticmethod
+    def _aligned(shape):
+        """64-byte aligned float32 array (what cudaMalloc gives the real kernels)."""
+        n = int(np.prod(shape))
+        raw = np.empty(n * 4 + 64, np.uint8)
+        off = (-raw.ctypes.data) % 64
+        return raw[off:off + n * 4].view(np.float32).reshape(shape)
+
     def up(self, a):
-        return np.ascontiguousarray(a, dtype=np.float32).copy()
+        b = self._aligned(np.shape(a))
+        b[...] = a
+        return b
 
     def empty(self, shape):
-        return np.full(shape, np.nan, np.float32)
+        b = self._aligned(shape)
+        b[...] = np.nan
+        return b
 
     def ptr(self, buf):
         return None if buf is None else buf.ctypes.data

@@ -122,7 +122,12 @@ def test_errors_are_loud(be):
 @pytest.mark.parametrize("border", [0, 1, 2])
 @pytest.mark.parametrize("shape,r", [((20, 64), 1), ((24, 100), 2), ((30, 40), 3), ((20, 520), 4), ((26, 36), 5),
                                      ((20, 48), 6), ((40, 133), 7), ((40, 600), 8), ((30, 64), 12), ((44, 500), 16)])
-def test_gray_fast(be, shape, r, border):
+def test_gray_fast(be, shape, r, border, monkeypatch):
+    monkeypatch.setenv("GF_DISABLE_S8", "1")
+    _gray_fast(be, shape, r, border)
+
+
+def _gray_fast(be, shape, r, border):
     """widths with w % 4 == 0 take the tuned kernel (128-bit row alignment); several strips
     (w > 480), warp-edge mailbox (every CTA has 4 warps), partial right edge, all borders."""
     I, p = synth_pair(*shape, seed=41, kind="structured")
@@ -133,7 +138,8 @@ def test_gray_fast(be, shape, r, border):
     assert np.abs(q - ref).max() <= TOL
 
 
-def test_gray_fast_ab_batch_strip(be):
+def test_gray_fast_ab_batch_strip(be, monkeypatch):
+    monkeypatch.setenv("GF_DISABLE_S8", "1")
     I, p = synth_pair(36, 64, seed=5)
     q, A, B = be.guided_gray(I, p, 4, 0.05, 0, want_ab=True)
     assert be.api.last_kernel() == "wp_r4"
@@ -156,7 +162,8 @@ def test_gray_fast_ab_batch_strip(be):
         assert np.abs(qs - ref[y0:y1]).max() <= TOL
 
 
-def test_kat_crop_u8_fast(be):
+def test_kat_crop_u8_fast(be, monkeypatch):
+    monkeypatch.setenv("GF_DISABLE_S8", "1")
     crop = [c for c in load_kat_crops() if c["name"] == "tl"][0]
     P, I = crop["P"][:60, :72], crop["I"][:60, :72]
     q = be.guided_gray(I, P, 7, 0.3, 0)
@@ -167,7 +174,8 @@ def test_kat_crop_u8_fast(be):
 
 @pytest.mark.parametrize("shape,r,border", [((24, 1452), 4, 0), ((120, 400), 8, 1), ((90, 400), 7, 2), ((70, 360), 3, 0),
                                             ((60, 1100), 16, 0), ((90, 1500), 20, 0)])
-def test_gray_fast_steady_path(be, shape, r, border):
+def test_gray_fast_steady_path(be, shape, r, border, monkeypatch):
+    monkeypatch.setenv("GF_DISABLE_S8", "1")
     """wide enough for a CTA strictly inside the image and tall enough for the straight-line
     steady-state loop (interior rows, 128-bit loads, constant normalisation) to run."""
     I, p = synth_pair(*shape, seed=51)
@@ -180,7 +188,48 @@ def test_gray_fast_steady_path(be, shape, r, border):
 def test_gray_wp_k8(be, shape, r, border, monkeypatch):
     """the 8-columns-per-lane build of the warp-private kernel (GF_WP_K8): interior and border warps."""
     monkeypatch.setenv("GF_WP_K8", "1")
+    monkeypatch.setenv("GF_DISABLE_S8", "1")
     I, p = synth_pair(*shape, seed=61, kind="structured")
     q = be.guided_gray(I, p, r, 1e-2, border)
     assert be.api.last_kernel() == f"wp8_r{r}"
     assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
+
+
+# ---- the headline kernel (gf_s8.cuh: 8 columns per lane) under the emulator ----------------------
+@pytest.mark.parametrize("shape,r,border", [((60, 700), 8, 0), ((75, 512), 8, 2), ((64, 256), 8, 0), ((50, 480), 8, 0), ((45, 472), 8, 0), ((40, 224), 8, 0), ((90, 1000), 8, 0),
+                                            ((50, 264), 7, 0), ((70, 520), 7, 2), ((30, 300), 4, 0), ((100, 640), 16, 0),
+                                            ((140, 456), 16, 2)])
+def test_gray_s8(be, shape, r, border, monkeypatch):
+    """interior and border strips (mapped loads), several bands (GF_S8_HB), a width that is not a
+    multiple of 8 (partial last lane), heights that end inside / right after a re-seed period."""
+    monkeypatch.setenv("GF_S8_HB", str(2 * r + 9))
+    I, p = synth_pair(*shape, seed=71, kind="structured")
+    w = shape[1]
+    q = be.guided_gray(I, p, r, 1e-2, border, pad=(-w) % 8)
+    assert be.api.last_kernel() == f"s8_r{r}"
+    assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
+
+
+def test_gray_s8_batch_strip_kat(be):
+    rng = np.random.default_rng(8)
+    Ib = rng.random((2, 40, 320), dtype=np.float32)
+    pb = rng.random((2, 40, 320), dtype=np.float32)
+    qb = be.batch(Ib, pb, 8, 1e-2, 0)
+    assert be.api.last_kernel() == "s8_r8"
+    for k in range(2):
+        assert np.abs(qb[k] - O.guided_filter_gray(Ib[k], pb[k], 8, 1e-2, 0)).max() <= TOL
+    # 3 row strips of a 96-row image, each seeing only its rows + the 2r halo
+    I, p = synth_pair(96, 264, seed=9)
+    ref = O.guided_filter_gray(I, p, 4, 1e-2, 0)
+    for s in range(3):
+        y0, y1 = 32 * s, 32 * (s + 1)
+        b0, b1 = max(0, y0 - 8), min(96, y1 + 8)
+        qs = be.strip(I[b0:b1], p[b0:b1], 264, 96, b0, y0, 32, 4, 1e-2, 0)
+        assert be.api.last_kernel() == "s8_r4"
+        assert np.abs(qs - ref[y0:y1]).max() <= TOL
+    crop = [c for c in load_kat_crops() if c["name"] == "tl"][0]
+    P, I = crop["P"][:60, :72], crop["I"][:60, :72]
+    q = be.guided_gray(I, P, 7, 0.3, 0)
+    assert be.api.last_kernel() == "s8_r7"
+    d = O.to_u8(q)[:32, :44].astype(int) - crop["gold"][:32, :44].astype(int)
+    assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 2
