@@ -95,6 +95,11 @@ def main():
             for (w, h, r) in [(7680, 4320, 8), (3840, 2160, 16), (7680, 4320, 16), (1920, 1080, 8)]:
                 out.append(time_gray(w, h, r, nsets=3 if w * h > 3e7 else 6, iters=20, env=env))
                 print(json.dumps(out[-1]), flush=True)
+    if cases and cases[0] == "custom":      # custom W H R [iters]  (kernel env vars come from the shell)
+        w, h, r = int(cases[1]), int(cases[2]), int(cases[3])
+        it = int(cases[4]) if len(cases) > 4 else 6
+        out.append(time_gray(w, h, r, nsets=2, iters=it))
+        print(json.dumps(out[-1]), flush=True)
     if "one" in cases:
         out.append(time_gray(3840, 2160, 8, iters=6))
         print(json.dumps(out[-1]), flush=True)
