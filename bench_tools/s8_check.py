@@ -76,9 +76,10 @@ def main():
     emit(sweep.time_gray(7680, 4320, 8, nsets=3, iters=20))
     emit(sweep.time_gray(16384, 8192, 8, nsets=2, iters=10))
     if mode == "full":
-        for (w, h, r) in [(1920, 1080, 8), (3840, 2160, 16), (7680, 4320, 16), (3840, 2160, 4), (3840, 2160, 7)]:
+        compare(7680, 4320, 32, 0)
+        for (w, h, r) in [(1920, 1080, 8), (3840, 2160, 16), (7680, 4320, 16), (3840, 2160, 4), (3840, 2160, 7), (7680, 4320, 32)]:
             emit(sweep.time_gray(w, h, r, nsets=3 if w * h > 3e7 else 6, iters=20))
-        emit(sweep.time_gray(3840, 2160, 8, env={"GF_DISABLE_S8": 1}))
+            emit(sweep.time_gray(w, h, r, nsets=3 if w * h > 3e7 else 6, iters=20, env={"GF_DISABLE_S8": 1}))
 
 
 if __name__ == "__main__":

@@ -187,6 +187,8 @@ struct GfS8Ctx {
     int lane, x0, width, height, border, buf_y0, buf_ylast, out_y0, yi0;
     bool vec_ok, ring_lane, out_lane;
     GfS8Edge edge;                                   // MODE 1 only
+    bool out_l, out_r;                               // MODE 3 only: lane lies left / right of the image
+    int vofs, sofs;                                  // MODE 3 only: vector / scalar source offsets relative to x0
     int sx[8];                                       // XMAP only: source column of each of the 8 columns, relative to x0
     float eps;
     GfNorm nk;                                       // 1 / (2R+1)^2
@@ -215,10 +217,30 @@ __device__ __forceinline__ float gf_s8_rcp(float d)
 #endif
 }
 
+// Strip modes: 0 interior; 1 analytic REFLECT101 image edges (R = 8); 3 mirror loads -- REFLECT101,
+// width % 8 == 0: a lane that lies outside the image reads the aligned 8-column group that holds
+// 7 of its 8 mirror columns plus one scalar, and permutes at compile time (no per-column gather);
+// 2 generic per-column border map (any border, any width; slow, rarely needed).
 template <int MODE, int R>
 __device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R>& c, const float* rowp, float2 (&v)[4])
 {
-    if (MODE != 2 || c.vec_ok) {
+    if (MODE == 3) {
+        float2 t[4];
+        gf_ld8(rowp + c.vofs, t);
+        const float sc = rowp[c.sofs];
+        const float e[8] = {t[0].x, t[0].y, t[1].x, t[1].y, t[2].x, t[2].y, t[3].x, t[3].y};
+        float d[8];
+        // left of the image:  column -8k+j <- column 8k-j   = {sc, e7, e6, .., e1}
+        // right of the image: column W+8m+j <- W-2-8m-j     = {e6, e5, .., e0, sc}
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float lv = j == 0 ? sc : e[8 - j];
+            const float rv = j == 7 ? sc : e[6 - j];
+            d[j] = c.out_l ? lv : (c.out_r ? rv : e[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = make_float2(d[2 * i], d[2 * i + 1]);
+    } else if (MODE != 2 || c.vec_ok) {
         gf_ld8(rowp, v);
     } else {
 #pragma unroll
@@ -334,7 +356,7 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
         const int oo = gf_s8_map_y(yi + 1 - KW, c.height, c.border) - c.buf_y0;
         gf_s8_ld<MODE>(c, c.gI + oo * c.gs, c.oI);
         gf_s8_ld<MODE>(c, c.gP + oo * c.ss, c.oP);
-        if (GF_S8_PF > 0 && !XMAP && lane < 8) {
+        if (GF_S8_PF > 0 && MODE <= 1 && lane < 8) {
             // L2 prefetch hint a few rows ahead: 8 lanes x one 128-byte line = the warp's 256 columns.
             // (Measured: +3% over no hint; a hint per 32-byte sector from all 32 lanes is 10% SLOWER.)
             const int rp = yi + 1 + GF_S8_PF;
@@ -434,7 +456,8 @@ __device__ __forceinline__ void gf_s8_band(GfS8Ctx<R>& c, int steps)
 // Strip geometry.  edge_ok (R = 8, REFLECT101, width % 8 == 0, width >= 256): the first strip
 // starts at column 0 and the last one ends at the last column, their image-side lanes use the
 // analytic mirror (MODE 1) and all their lanes on that side produce output.  Otherwise strips
-// that overhang the image load through the per-column border map (MODE 2).
+// that overhang the image use mirror loads (MODE 3: REFLECT101, width % 8 == 0) or the generic
+// per-column border map (MODE 2).
 template <int R, int MINB>
 __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
 {
@@ -457,7 +480,7 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
         if (first) { xl = 0; lane_lo = 0; }
         if (last && !first) { xl = a.width - G::WIN; lane_lo = 4 * H1; col_min = strip * G::WOUT; }
     } else if (xl < 0 || xl + G::WIN > a.width) {
-        mode = 2;
+        mode = (a.border == GF_REFLECT101 && (a.width & 7) == 0 && a.width >= G::WIN) ? 3 : 2;
     }
     c.x0 = xl + 8 * c.lane;
     c.edge.left = mode == 1 && first && c.lane == 0;
@@ -473,6 +496,10 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
         c.buf_ylast = yl < a.height - 1 ? yl : a.height - 1;
     }
     c.vec_ok = c.x0 >= 0 && c.x0 + 7 < a.width;
+    c.out_l = mode == 3 && c.x0 < 0;
+    c.out_r = mode == 3 && c.x0 >= a.width;
+    c.vofs = c.out_l ? -2 * c.x0 - 8 : (c.out_r ? 2 * a.width - 8 - 2 * c.x0 : 0);
+    c.sofs = c.out_l ? -2 * c.x0 : (c.out_r ? 2 * a.width - 9 - 2 * c.x0 : 0);
     const int yo0 = a.out_y0 + band * a.hb;
     const int yo1 = min(a.out_y0 + a.out_rows, yo0 + a.hb);
     c.yi0 = yo0 - 2 * R;
@@ -492,6 +519,9 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
     if (mode == 2) {
         gf_s8_ld<2>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<2>(c, c.gP + o0 * c.ss, c.nP);
         gf_s8_band<R, 2>(c, steps);
+    } else if (mode == 3) {
+        gf_s8_ld<3>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<3>(c, c.gP + o0 * c.ss, c.nP);
+        gf_s8_band<R, 3>(c, steps);
     } else {
         gf_s8_ld<0>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<0>(c, c.gP + o0 * c.ss, c.nP);
         if constexpr (R == 8) {
@@ -542,7 +572,8 @@ static const char* gf_s8_launch(const Job& j)
     a.nbands = (j.out_rows + hb - 1) / hb;
     const long items = (long)a.nstrips * a.nbands * j.count;
     dim3 grid((unsigned)items), block(32);
-    constexpr int MINB = G::ring_bytes * 7 + 7 * 1024 <= 228 * 1024 ? 7 : (G::ring_bytes * 4 + 4 * 1024 <= 228 * 1024 ? 4 : 2);
+    constexpr int FIT = (int)((size_t)228 * 1024 / (G::ring_bytes + 1024));
+    constexpr int MINB = FIT > 7 ? 7 : (FIT < 1 ? 1 : FIT);
     auto k = gf_s8_gray_kernel<R, MINB>;
     if (const char* e = gf_rt_set_smem(k, smem)) return e;
     GF_LAUNCH(k, grid, block, smem, j.stream, a);
@@ -570,6 +601,7 @@ static const char* gf_s8_try(const Job& j, bool* done, const char** name)
     case 7: *done = true; *name = "s8_r7"; return gf_s8_launch<7>(j);
     case 8: *done = true; *name = "s8_r8"; return gf_s8_launch<8>(j);
     case 16: *done = true; *name = "s8_r16"; return gf_s8_launch<16>(j);
+    case 32: *done = true; *name = "s8_r32"; return gf_s8_launch<32>(j);
     default: return nullptr;
     }
 }

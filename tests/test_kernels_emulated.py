@@ -197,7 +197,7 @@ def test_gray_wp_k8(be, shape, r, border, monkeypatch):
 
 # ---- the headline kernel (gf_s8.cuh: 8 columns per lane) under the emulator ----------------------
 @pytest.mark.parametrize("shape,r,border", [((60, 700), 8, 0), ((75, 512), 8, 2), ((64, 256), 8, 0), ((50, 480), 8, 0), ((45, 472), 8, 0), ((40, 224), 8, 0), ((90, 1000), 8, 0),
-                                            ((50, 264), 7, 0), ((70, 520), 7, 2), ((30, 300), 4, 0), ((100, 640), 16, 0),
+                                            ((50, 264), 7, 0), ((70, 520), 7, 2), ((30, 300), 4, 0), ((40, 320), 4, 0), ((100, 640), 16, 0), ((140, 512), 32, 0),
                                             ((140, 456), 16, 2)])
 def test_gray_s8(be, shape, r, border, monkeypatch):
     """interior and border strips (mapped loads), several bands (GF_S8_HB), a width that is not a
