@@ -597,11 +597,10 @@ static const char* gf_s8_try(const Job& j, bool* done, const char** name)
     // single reflections only, and at least one full warp window of columns
     if (j.height < 4 * j.r + 2 || j.width < 4 * j.r + 2 || j.width < 64) return nullptr;
     switch (j.r) {
-    case 4: *done = true; *name = "s8_r4"; return gf_s8_launch<4>(j);
-    case 7: *done = true; *name = "s8_r7"; return gf_s8_launch<7>(j);
-    case 8: *done = true; *name = "s8_r8"; return gf_s8_launch<8>(j);
-    case 16: *done = true; *name = "s8_r16"; return gf_s8_launch<16>(j);
-    case 32: *done = true; *name = "s8_r32"; return gf_s8_launch<32>(j);
+#define GF_S8_CASE(RR) case RR: *done = true; *name = "s8_r" #RR; return gf_s8_launch<RR>(j);
+    GF_S8_CASE(1) GF_S8_CASE(2) GF_S8_CASE(3) GF_S8_CASE(4) GF_S8_CASE(5) GF_S8_CASE(6) GF_S8_CASE(7) GF_S8_CASE(8)
+    GF_S8_CASE(10) GF_S8_CASE(12) GF_S8_CASE(16) GF_S8_CASE(20) GF_S8_CASE(24) GF_S8_CASE(32)
+#undef GF_S8_CASE
     default: return nullptr;
     }
 }

@@ -5,7 +5,8 @@
 // `integral` scratch of hBoxFilter is ignored (window sums are exact, not a float32 integral
 // image); hCalcB with a 1-channel guide computes b = pm - a*im (the reference's gCalcBCN1 does
 // not, guided_filter_d.cu:371-372); hGuidedFilter accepts any radius (the reference silently
-// does nothing outside 1..7, :1090).
+// does nothing outside 1..7, :1090) and leaves its d_A / d_B scratch planes untouched -- a and b never
+// leave the SM in the fused kernel; set GF_SHIM_FILL_AB=1 in the environment to have them written.
 #pragma once
 #include "cuda_utils.h"
 

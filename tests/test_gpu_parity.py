@@ -43,6 +43,39 @@ def test_gray_small_vs_oracle(be, shape, r, border):
     assert np.abs(q - ref).max() <= TOL
 
 
+S8_RADII = (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32)
+
+
+@pytest.mark.parametrize("border", [0, 2])
+@pytest.mark.parametrize("r", S8_RADII)
+def test_gray_s8_every_radius(be, r, border):
+    """The headline kernel family (gf_s8.cuh) at every radius it is instantiated for: interior
+    strips, border strips (analytic edges at r=8, mirror loads for REFLECT101, the generic column
+    map for REFLECT), several bands, a width that is / is not a multiple of 8."""
+    for (h, w) in ((300, 960), (270, 1004)):
+        I, p = synth_pair(h, w, seed=100 + r, kind="structured")
+        q = be.guided_gray(I, p, r, 1e-2, border, pad=(-w) % 8)
+        assert be.api.last_kernel() == f"s8_r{r}"
+        ref = C.guided_gray_f64(I, p, r, 1e-2, border, NT)
+        assert np.abs(q - ref).max() <= TOL
+
+
+def test_gray_8k_r8_and_giga_strip_r16(be):
+    """Larger-than-4K frames take the multi-wave path of the s8 kernel (bands of hb_max rows);
+    a 4096-row strip of a 32768-wide image is the per-GPU unit of BASELINE config 5 (r=16)."""
+    I, p = synth_pair(4320, 7680, seed=4)
+    q = be.guided_gray(I, p, 8, 1e-2, 0)
+    assert be.api.last_kernel() == "s8_r8"
+    assert np.abs(q - C.guided_gray_f64(I, p, 8, 1e-2, 0, NT)).max() <= TOL
+    del I, p, q
+    w, hs, r = 32768, 1024, 16                      # 1024 rows of the strip keep the oracle fast
+    I, p = synth_pair(hs + 4 * r, w, seed=6)
+    q = be.strip(I, p, w, 32768, 8192 - 2 * r, 8192, hs, r, 1e-2, 0)
+    assert be.api.last_kernel() == "s8_r16"
+    ref = C.guided_gray_f64(I, p, r, 1e-2, 0, NT)[2 * r:2 * r + hs]
+    assert np.abs(q - ref).max() <= TOL
+
+
 @pytest.mark.parametrize("kind", ["noise", "structured"])
 @pytest.mark.parametrize("border", [0, 1])
 def test_gray_4k_r8(be, kind, border):
@@ -206,14 +239,20 @@ def test_host_entry_and_dropin_program(be, tmp_path):
         f.write(np.float32(eps).tobytes())
         f.write(g.tobytes())
         f.write(s.tobytes())
-    subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
-    out = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
     n = w * h
-    q_class = out[:n * sch].reshape(h, w, sch)
-    q_fused, A, B = (out[n * sch + i * n: n * sch + (i + 1) * n].reshape(h, w) for i in range(3))
-    assert np.abs(q_class - O.guided_filter_class_run(g, s, r, eps)).max() <= TOL
     rq, ra, rb = O.guided_filter_gray(g, s[:, :, 0], r, eps, 0, np.float64, return_ab=True)
-    assert np.abs(q_fused - rq).max() <= TOL and np.abs(A - ra).max() <= TOL and np.abs(B - rb).max() <= TOL
+    for fill_ab in (False, True):
+        env = dict(os.environ)
+        if fill_ab:
+            env["GF_SHIM_FILL_AB"] = "1"        # hGuidedFilter's d_A / d_B are scratch: written only on request
+        subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], env=env)
+        out = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
+        q_class = out[:n * sch].reshape(h, w, sch)
+        q_fused, A, B = (out[n * sch + i * n: n * sch + (i + 1) * n].reshape(h, w) for i in range(3))
+        assert np.abs(q_class - O.guided_filter_class_run(g, s, r, eps)).max() <= TOL
+        assert np.abs(q_fused - rq).max() <= TOL
+        if fill_ab:
+            assert np.abs(A - ra).max() <= TOL and np.abs(B - rb).max() <= TOL
 
 
 def test_against_reference_gpu_code(be):
