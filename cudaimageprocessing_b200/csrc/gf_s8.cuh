@@ -284,7 +284,47 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
     const int yi = c.yi0 + t;
     const int lane = c.lane;
 
-    // ================= phase A: stage 2 of centre row yi-1-R =================
+    // ================= phase B, part 1: vertical sums of row yi =================
+    // (first, so that the loads of the next iteration can be issued right away and have a whole
+    // iteration to land)
+    float2 gI[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gI[i] = c.oI[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c.cI[i] = gf_add2(c.cI[i], gf_sub2(c.nI[i], c.oI[i]));
+        c.cP[i] = gf_add2(c.cP[i], gf_sub2(c.nP[i], c.oP[i]));
+        c.cIP[i] = gf_fma2(gf_neg2(c.oI[i]), c.oP[i], gf_fma2(c.nI[i], c.nP[i], c.cIP[i]));
+        c.cII[i] = gf_fma2(gf_neg2(c.oI[i]), c.oI[i], gf_fma2(c.nI[i], c.nI[i], c.cII[i]));
+        if (GF_S8_RESEED1) {
+            c.fI[i] = gf_add2(c.fI[i], c.nI[i]);
+            c.fP[i] = gf_add2(c.fP[i], c.nP[i]);
+            c.fIP[i] = gf_fma2(c.nI[i], c.nP[i], c.fIP[i]);
+            c.fII[i] = gf_fma2(c.nI[i], c.nI[i], c.fII[i]);
+        }
+    }
+    // rows of the next iteration, consumed at the top of it
+    if (!(GF_S8_ABL & 4)) {
+        int rn = gf_s8_map_y(yi + 1, c.height, c.border);
+        rn = rn > c.buf_ylast ? c.buf_ylast : rn;
+        const int on = rn - c.buf_y0;
+        gf_s8_ld<MODE>(c, c.gI + on * c.gs, c.nI);
+        gf_s8_ld<MODE>(c, c.gP + on * c.ss, c.nP);
+        const int oo = gf_s8_map_y(yi + 1 - KW, c.height, c.border) - c.buf_y0;
+        gf_s8_ld<MODE>(c, c.gI + oo * c.gs, c.oI);
+        gf_s8_ld<MODE>(c, c.gP + oo * c.ss, c.oP);
+        if (GF_S8_PF > 0 && MODE <= 1 && lane < 8) {
+            // L2 prefetch hint a few rows ahead: 8 lanes x one 128-byte line = the warp's 256 columns.
+            // (Measured: +3% over no hint; a hint per 32-byte sector from all 32 lanes is 10% SLOWER.)
+            const int rp = yi + 1 + GF_S8_PF;
+            if (rp <= c.buf_ylast) {
+                const int op = rp - c.buf_y0;
+                gf_prefetch_l2(c.gI + op * c.gs + 24 * lane);
+                gf_prefetch_l2(c.gP + op * c.ss + 24 * lane);
+            }
+        }
+    }
+    // ================= phase A: stage 2 of centre row yi-1-R (guide row of its output: gI) =================
     {
         float2 hA[4], hB[4];
         gf_s8_window<R, EDGE>(c.va, hA, lane, c.edge);
@@ -314,7 +354,7 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
             const float2 nh = gf_dup2(c.nk.hi), nl = gf_dup2(c.nk.lo);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float2 v = gf_fma2(c.sA[i], c.oI[i], c.sB[i]);
+                const float2 v = gf_fma2(c.sA[i], gI[i], c.sB[i]);
                 q[i] = gf_fma2(v, nh, gf_mul2(v, nl));
             }
             float* pq = c.gQ + (yo - c.out_y0) * c.ds;
@@ -332,41 +372,7 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
         }
     }
 
-    // ================= phase B: stage 1 of row yi =================
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        c.cI[i] = gf_add2(c.cI[i], gf_sub2(c.nI[i], c.oI[i]));
-        c.cP[i] = gf_add2(c.cP[i], gf_sub2(c.nP[i], c.oP[i]));
-        c.cIP[i] = gf_fma2(gf_neg2(c.oI[i]), c.oP[i], gf_fma2(c.nI[i], c.nP[i], c.cIP[i]));
-        c.cII[i] = gf_fma2(gf_neg2(c.oI[i]), c.oI[i], gf_fma2(c.nI[i], c.nI[i], c.cII[i]));
-        if (GF_S8_RESEED1) {
-            c.fI[i] = gf_add2(c.fI[i], c.nI[i]);
-            c.fP[i] = gf_add2(c.fP[i], c.nP[i]);
-            c.fIP[i] = gf_fma2(c.nI[i], c.nP[i], c.fIP[i]);
-            c.fII[i] = gf_fma2(c.nI[i], c.nI[i], c.fII[i]);
-        }
-    }
-    // rows of the next iteration, consumed a full iteration later
-    if (!(GF_S8_ABL & 4)) {
-        int rn = gf_s8_map_y(yi + 1, c.height, c.border);
-        rn = rn > c.buf_ylast ? c.buf_ylast : rn;
-        const int on = rn - c.buf_y0;
-        gf_s8_ld<MODE>(c, c.gI + on * c.gs, c.nI);
-        gf_s8_ld<MODE>(c, c.gP + on * c.ss, c.nP);
-        const int oo = gf_s8_map_y(yi + 1 - KW, c.height, c.border) - c.buf_y0;
-        gf_s8_ld<MODE>(c, c.gI + oo * c.gs, c.oI);
-        gf_s8_ld<MODE>(c, c.gP + oo * c.ss, c.oP);
-        if (GF_S8_PF > 0 && MODE <= 1 && lane < 8) {
-            // L2 prefetch hint a few rows ahead: 8 lanes x one 128-byte line = the warp's 256 columns.
-            // (Measured: +3% over no hint; a hint per 32-byte sector from all 32 lanes is 10% SLOWER.)
-            const int rp = yi + 1 + GF_S8_PF;
-            if (rp <= c.buf_ylast) {
-                const int op = rp - c.buf_y0;
-                gf_prefetch_l2(c.gI + op * c.gs + 24 * lane);
-                gf_prefetch_l2(c.gP + op * c.ss + 24 * lane);
-            }
-        }
-    }
+    // ================= phase B, part 2 =================
     {
         // horizontal -> a, b of row yi - R.  Every window is full (REFLECT borders mirror the data):
         //   a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2),   b = (S_p - a S_I) / N
