@@ -19,6 +19,7 @@
 #include "gf_fast.cuh"
 #include "gf_wp.cuh"
 #include "gf_s8.cuh"
+#include "gf_c4.cuh"
 #endif
 
 namespace {
@@ -174,7 +175,8 @@ int run_job(const Job& j)
 #ifdef GF_HAVE_FAST
     {
         const char* name = nullptr;
-        const char* e = gf_s8_try(j, &done, &name);
+        const char* e = gf_c4_try(j, &done, &name);
+        if (!done) e = gf_s8_try(j, &done, &name);
         if (!done) e = gf_wp_try(j, &done, &name);
         if (!done) e = gf_fast_try(j, &done, &name);
         if (done) {

@@ -1,0 +1,389 @@
+// gf_c4.cuh -- tuned colour-guide kernel (3-channel interleaved guide, 1-channel src/dst, float32):
+// the 3x3-covariance guided filter of He et al. (TPAMI 2013, eqs. 19-21), fused in one pass.
+// The reference has no colour-guide implementation (guided_filter_d.cu:976-979 refuses it); the
+// arithmetic follows oracle/gf_oracle.py::guided_filter_color and GfColorModel (gf_generic.cuh).
+//
+// Same architecture as gf_s8.cuh, sized for 13 + 4 box-filtered quantities instead of 4 + 2:
+//   * every WARP is an independent worker; a lane owns 4 ADJACENT columns (13 x 4 vertical running
+//     sums in registers; 8 columns per lane would need 104 and spill);
+//   * stage 1: vertical running sums of I_r, I_g, I_b, p, I_c p (3), I_c I_d (6); horizontal
+//     (2R+1)-window sums across lanes with the folded scheme of gf_s8 (left term = suffix of lane
+//     l-M extended by the totals of the 2M-1 lanes in between, right term = prefix of lane l+M,
+//     M = R/4; 13 shuffles and 15 additions per quantity and 4 pixels at R = 16, additions only);
+//     per pixel the symmetric 3x3 system (Sigma + eps U) a = cov(I, p) by cofactors;
+//   * stage 2: window sums of a_r, a_g, a_b, b, vertical running sums through a (2R+1)-row ring in
+//     shared memory (one float4 per lane, quantity and row: conflict-free LDS.128/STS.128);
+//   * q = mean_a . I + mean_b; the guide row of the output is the row that leaves the stage-1
+//     window in the same iteration (re-read from L2, never parked);
+//   * image borders (REFLECT101, width % 4 == 0): lanes outside the image take their rows from
+//     the mirror lanes by shuffle (32 extra SHFL per iteration, border strips only); any other
+//     border/width uses the generic kernel.
+// R must be a multiple of 4 and <= 16 (M <= 4 halo lanes per side and stage).
+#pragma once
+#include "gf_s8.cuh"
+
+template <int R>
+struct GfC4Geom {
+    static constexpr int M = R / 4;                  // halo lanes per side per stage
+    static constexpr int VL = 32 - 4 * M;            // lanes that produce output
+    static constexpr int WOUT = 4 * VL;              // output columns per warp
+    static constexpr int WIN = 128;                  // columns a warp loads
+    static constexpr int KW = 2 * R + 1;
+    static constexpr int SLOT_F4 = 4 * VL;           // float4 per ring row: [q][cell]
+    static constexpr size_t ring_bytes = (size_t)KW * SLOT_F4 * 16;
+};
+
+// (2R+1)-window sums of the 4 columns of every lane; complete for lanes [M, 32-M).
+template <int R>
+__device__ __forceinline__ void gf_c4_window(const float (&x)[4], float (&w)[4])
+{
+    constexpr int M = R / 4;
+    static_assert(R % 4 == 0 && M >= 1 && M <= 4, "gf_c4 needs R = 4, 8, 12 or 16");
+    const unsigned full = 0xffffffffu;
+    const float p0 = x[0], p1 = x[0] + x[1], p2 = p1 + x[2], T = (x[0] + x[1]) + (x[2] + x[3]);
+    // e = T(l+1) + .. + T(l+2M-1)
+    float e;
+    if (M == 1) {
+        e = __shfl_down_sync(full, T, 1);
+    } else {
+        const float u2 = T + __shfl_down_sync(full, T, 1);                     // T(l..l+1)
+        float s;                                                               // T(l..l+2M-2)
+        if (M == 2) s = u2 + __shfl_down_sync(full, T, 2);
+        else if (M == 3) s = (u2 + __shfl_down_sync(full, u2, 2)) + __shfl_down_sync(full, T, 4);
+        else s = (u2 + __shfl_down_sync(full, u2, 2)) + (__shfl_down_sync(full, u2, 4) + __shfl_down_sync(full, T, 6));
+        e = __shfl_down_sync(full, s, 1);
+    }
+    const float a3 = x[3] + e, a2 = (x[2] + x[3]) + e, a1 = x[1] + a2, a0 = T + e;
+    const float l0 = __shfl_up_sync(full, a0, M), l1 = __shfl_up_sync(full, a1, M), l2 = __shfl_up_sync(full, a2, M),
+                l3 = __shfl_up_sync(full, a3, M);
+    const float r0 = __shfl_down_sync(full, p0, M), r1 = __shfl_down_sync(full, p1, M), r2 = __shfl_down_sync(full, p2, M),
+                r3 = __shfl_down_sync(full, T, M);
+    w[0] = l0 + r0; w[1] = l1 + r1; w[2] = l2 + r2; w[3] = l3 + r3;
+}
+
+template <int R>
+struct GfC4Ctx {
+    const float* gI; const float* gP; float* gQ;     // frame bases at this lane's first column (gI: 3 floats per column)
+    int gs, ss, ds;
+    float4* ring;
+    int lane, x0, width, height, border, buf_y0, buf_ylast, out_y0, yi0;
+    bool ring_lane, out_lane, mirror, out_l, out_r, src_l;   // mirror: this warp overhangs the image
+    int s0, s1, s2;                                  // mirror source lanes for column j = 0, j = 1..2, j = 3
+    float eps;
+    float c[13][4];                                  // stage-1 column sums
+    float sa[4][4];                                  // stage-2 running sums (a_r, a_g, a_b, b)
+    float va[4][4];                                  // a, b of the row produced by the previous iteration
+    float nI[12], nP[4], oI[12], oP[4];              // newest row / row leaving the window (= guide row of the output)
+};
+
+// Raw loads of one row: 12 guide floats (3 x LDG.128) and 4 src floats.  A lane outside the image
+// loads its mirror lane's address instead (any valid address would do) and is patched by gf_c4_mirror.
+template <int R>
+__device__ __forceinline__ void gf_c4_ld(const GfC4Ctx<R>& c, int row_ofs_I, int row_ofs_P, float (&vi)[12], float (&vp)[4])
+{
+    const float4* pi = reinterpret_cast<const float4*>(c.gI + row_ofs_I);
+    const float4 t0 = pi[0], t1 = pi[1], t2 = pi[2];
+    const float4 tp = *reinterpret_cast<const float4*>(c.gP + row_ofs_P);
+    vi[0] = t0.x; vi[1] = t0.y; vi[2] = t0.z; vi[3] = t0.w; vi[4] = t1.x; vi[5] = t1.y; vi[6] = t1.z; vi[7] = t1.w;
+    vi[8] = t2.x; vi[9] = t2.y; vi[10] = t2.z; vi[11] = t2.w;
+    vp[0] = tp.x; vp[1] = tp.y; vp[2] = tp.z; vp[3] = tp.w;
+}
+
+// REFLECT101 mirror for lanes outside the image (width % 4 == 0):
+//   left : column -4k+j <- column 4k-j      = {col0 of lane s0, col3, col2, col1 of lane s1}
+//   right: column W+4m+j <- column W-2-4m-j = {col2, col1, col0 of lane s1(=s0), col3 of lane s2}
+// A warp overhangs at most one side (width >= 128), so all its lanes publish that side's pattern.
+template <int R>
+__device__ __forceinline__ void gf_c4_mirror(const GfC4Ctx<R>& c, float (&vi)[12], float (&vp)[4])
+{
+    const unsigned full = 0xffffffffu;
+    const bool out = c.out_l || c.out_r;
+    // per destination column j: source column index in the source lane (left pattern / right pattern)
+    //   j:      0  1  2  3
+    //   left:   0  3  2  1      lanes: s0 s1 s1 s1
+    //   right:  2  1  0  3      lanes: s0 s0 s0 s2   (s1 == s0 for right lanes)
+    float ni[12], np[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int jl = j == 0 ? 0 : 4 - j, jr = j == 3 ? 3 : 2 - j;
+        const int sl = j == 0 ? c.s0 : c.s1;
+        const int sr = j == 3 ? c.s2 : c.s0;
+        const int srcl = c.out_l ? sl : sr;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float pub = c.src_l ? vi[3 * jl + ch] : vi[3 * jr + ch];
+            ni[3 * j + ch] = __shfl_sync(full, pub, srcl);
+        }
+        const float pubp = c.src_l ? vp[jl] : vp[jr];
+        np[j] = __shfl_sync(full, pubp, srcl);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) vi[i] = out ? ni[i] : vi[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) vp[j] = out ? np[j] : vp[j];
+}
+
+template <int R, bool MIRROR>
+__device__ __forceinline__ void gf_c4_load_row(const GfC4Ctx<R>& c, int y, float (&vi)[12], float (&vp)[4])
+{
+    int rn = gf_s8_map_y(y, c.height, c.border);
+    rn = rn > c.buf_ylast ? c.buf_ylast : rn;
+    const int o = rn - c.buf_y0;
+    gf_c4_ld<R>(c, o * c.gs, o * c.ss, vi, vp);
+    if (MIRROR) gf_c4_mirror<R>(c, vi, vp);
+}
+
+// the 13 products of one pixel, added to (SUB = false) or removed from (SUB = true) the column sums
+template <bool SUB>
+__device__ __forceinline__ void gf_c4_accum(float (&c)[13][4], int j, float i0, float i1, float i2, float p)
+{
+    const float s = SUB ? -1.f : 1.f;
+    c[0][j] += s * i0; c[1][j] += s * i1; c[2][j] += s * i2; c[3][j] += s * p;
+    const float m0 = s * i0, m1 = s * i1, m2 = s * i2;
+    c[4][j] = fmaf(m0, p, c[4][j]); c[5][j] = fmaf(m1, p, c[5][j]); c[6][j] = fmaf(m2, p, c[6][j]);
+    c[7][j] = fmaf(m0, i0, c[7][j]); c[8][j] = fmaf(m0, i1, c[8][j]); c[9][j] = fmaf(m0, i2, c[9][j]);
+    c[10][j] = fmaf(m1, i1, c[10][j]); c[11][j] = fmaf(m1, i2, c[11][j]); c[12][j] = fmaf(m2, i2, c[12][j]);
+}
+
+// Iteration t >= 2R (see gf_s8_iter for the schedule: ramp-up is data, not code).
+template <int R, bool MIRROR>
+__device__ __forceinline__ void gf_c4_iter(GfC4Ctx<R>& c, int t, int slot, bool full)
+{
+    using G = GfC4Geom<R>;
+    constexpr int KW = G::KW, VL = G::VL;
+    const int yi = c.yi0 + t;
+
+    // ---- stage 1, vertical: add row yi, drop row yi - KW (its guide pixels are kept for the output)
+    float gI[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) gI[i] = c.oI[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        gf_c4_accum<false>(c.c, j, c.nI[3 * j], c.nI[3 * j + 1], c.nI[3 * j + 2], c.nP[j]);
+        gf_c4_accum<true>(c.c, j, c.oI[3 * j], c.oI[3 * j + 1], c.oI[3 * j + 2], c.oP[j]);
+    }
+    // rows of the next iteration
+    gf_c4_load_row<R, MIRROR>(c, yi + 1, c.nI, c.nP);
+    gf_c4_load_row<R, MIRROR>(c, yi + 1 - KW, c.oI, c.oP);
+
+    // ---- stage 2 of the a, b row produced by the previous iteration
+    {
+        float h[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gf_c4_window<R>(c.va[q], h[q]);
+        if (c.ring_lane) {
+            float4* s = c.ring + slot * G::SLOT_F4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (full) {
+                    const float4 o = s[q * VL];
+                    c.sa[q][0] += h[q][0] - o.x; c.sa[q][1] += h[q][1] - o.y; c.sa[q][2] += h[q][2] - o.z; c.sa[q][3] += h[q][3] - o.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) c.sa[q][j] += h[q][j];
+                }
+                s[q * VL] = make_float4(h[q][0], h[q][1], h[q][2], h[q][3]);
+            }
+        }
+        if (full) {                                   // q of row yo = yi-1-2R; guide row gI
+            const int yo = yi - 1 - 2 * R;
+            const float inv = 1.0f / (float)(KW * KW);
+            float qv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float v = fmaf(c.sa[0][j], gI[3 * j], fmaf(c.sa[1][j], gI[3 * j + 1], fmaf(c.sa[2][j], gI[3 * j + 2], c.sa[3][j])));
+                qv[j] = v * inv;
+            }
+            if (c.out_lane) *reinterpret_cast<float4*>(c.gQ + (yo - c.out_y0) * c.ds) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+        }
+    }
+
+    // ---- stage 1, horizontal -> a, b of row yi - R
+    {
+        float h[13][4];
+#pragma unroll
+        for (int q = 0; q < 13; ++q) gf_c4_window<R>(c.c[q], h[q]);
+        const float inv = 1.0f / (float)(KW * KW);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float m0 = h[0][j] * inv, m1 = h[1][j] * inv, m2 = h[2][j] * inv, mp = h[3][j] * inv;
+            const float c0 = fmaf(h[4][j], inv, -m0 * mp), c1 = fmaf(h[5][j], inv, -m1 * mp), c2 = fmaf(h[6][j], inv, -m2 * mp);
+            const float s00 = fmaf(h[7][j], inv, -m0 * m0) + c.eps, s01 = fmaf(h[8][j], inv, -m0 * m1),
+                        s02 = fmaf(h[9][j], inv, -m0 * m2), s11 = fmaf(h[10][j], inv, -m1 * m1) + c.eps,
+                        s12 = fmaf(h[11][j], inv, -m1 * m2), s22 = fmaf(h[12][j], inv, -m2 * m2) + c.eps;
+            const float i00 = s11 * s22 - s12 * s12, i01 = s02 * s12 - s01 * s22, i02 = s01 * s12 - s02 * s11,
+                        i11 = s00 * s22 - s02 * s02, i12 = s01 * s02 - s00 * s12, i22 = s00 * s11 - s01 * s01;
+            const float det = s00 * i00 + s01 * i01 + s02 * i02;
+            float rd = gf_s8_rcp(det);
+            rd = fmaf(fmaf(-det, rd, 1.0f), rd, rd);
+            const float a0 = (i00 * c0 + i01 * c1 + i02 * c2) * rd;
+            const float a1 = (i01 * c0 + i11 * c1 + i12 * c2) * rd;
+            const float a2 = (i02 * c0 + i12 * c1 + i22 * c2) * rd;
+            c.va[0][j] = a0; c.va[1][j] = a1; c.va[2][j] = a2;
+            c.va[3][j] = mp - (a0 * m0 + a1 * m1 + a2 * m2);
+        }
+    }
+}
+
+template <int R, bool MIRROR>
+__device__ __forceinline__ void gf_c4_band(GfC4Ctx<R>& c, int steps)
+{
+    constexpr int KW = 2 * R + 1;
+    // warm-up rows t in [0, 2R): vertical accumulation only, two rows in flight
+    {
+        float bI[12], bP[4];
+#pragma unroll 1
+        for (int t = 0; t < 2 * R; t += 2) {
+            gf_c4_load_row<R, MIRROR>(c, c.yi0 + t + 1, bI, bP);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gf_c4_accum<false>(c.c, j, c.nI[3 * j], c.nI[3 * j + 1], c.nI[3 * j + 2], c.nP[j]);
+            gf_c4_load_row<R, MIRROR>(c, c.yi0 + t + 2, c.nI, c.nP);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gf_c4_accum<false>(c.c, j, bI[3 * j], bI[3 * j + 1], bI[3 * j + 2], bP[j]);
+        }
+    }
+    int t = 2 * R;
+    bool full = false;
+#pragma unroll 1
+    while (t <= steps) {
+        const int n = steps + 1 - t < KW ? steps + 1 - t : KW;
+#pragma unroll 1
+        for (int s = 0; s < n; ++s, ++t) gf_c4_iter<R, MIRROR>(c, t, s, full);
+        full = true;
+    }
+}
+
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) gf_c4_color_kernel(const GfWpArgs a)
+{
+    using G = GfC4Geom<R>;
+    constexpr int M = G::M, VL = G::VL;
+    GF_DYN_SMEM(float, smem);
+    const long item = (long)blockIdx.x;
+    const long per_frame = (long)a.nstrips * a.nbands;
+    const int64_t f = item / per_frame;
+    const int band = (int)((item % per_frame) / a.nstrips), strip = (int)(item % a.nstrips);
+
+    GfC4Ctx<R> c;
+    c.lane = threadIdx.x & 31;
+    const int xl = strip * G::WOUT - 2 * M * 4;
+    c.x0 = xl + 4 * c.lane;
+    c.mirror = xl < 0 || xl + G::WIN > a.width;
+    c.out_l = c.x0 < 0;
+    c.out_r = c.x0 >= a.width;
+    // mirror source lanes (see gf_c4_mirror)
+    {
+        const int lw = (a.width - xl) / 4 - 1;       // last lane inside the image (may be >= 32: then no lane is out_r)
+        const int X = 4 * M - c.lane;                // left: lane of column -x0 (j = 0)
+        const int Y = 2 * lw + 1 - c.lane;           // right: lane of column W-2-(x0-W) (j = 0..2)
+        c.s0 = c.out_l ? X : Y;
+        c.s1 = c.out_l ? X - 1 : Y;
+        c.s2 = Y - 1;
+        // lanes far outside the image (beyond the 2M halo lanes) mirror nothing anyone uses: clamp
+        // their sources to lanes inside the image so that every shuffle and address stays valid
+        const int lo_in = xl < 0 ? 2 * M : 0, hi_in = lw < 31 ? lw : 31;
+        c.s0 = c.s0 < lo_in ? lo_in : (c.s0 > hi_in ? hi_in : c.s0);
+        c.s1 = c.s1 < lo_in ? lo_in : (c.s1 > hi_in ? hi_in : c.s1);
+        c.s2 = c.s2 < lo_in ? lo_in : (c.s2 > hi_in ? hi_in : c.s2);
+        c.src_l = xl < 0;                            // width >= 128: a warp overhangs at most one side of the image
+    }
+    // lanes outside the image load from a valid address (their mirror lane's); the data is replaced
+    const int xa = (c.out_l || c.out_r) ? 4 * c.s0 + xl : c.x0;
+    c.gI = a.guide + f * a.gfs + (int64_t)3 * xa; c.gP = a.src + f * a.sfs + xa; c.gQ = a.dst + f * a.dfs + c.x0;
+    c.gs = (int)a.gs; c.ss = (int)a.ss; c.ds = (int)a.ds;
+    c.ring_lane = c.lane >= 2 * M && c.lane < 32 - 2 * M;
+    c.out_lane = c.ring_lane && c.x0 < a.width;
+    c.ring = reinterpret_cast<float4*>(smem) + (c.ring_lane ? c.lane - 2 * M : 0);
+    c.width = a.width; c.height = a.height; c.border = a.border; c.buf_y0 = a.buf_y0; c.out_y0 = a.out_y0;
+    {
+        const int yl = a.buf_y0 + a.buf_rows - 1;
+        c.buf_ylast = yl < a.height - 1 ? yl : a.height - 1;
+    }
+    const int yo0 = a.out_y0 + band * a.hb;
+    const int yo1 = min(a.out_y0 + a.out_rows, yo0 + a.hb);
+    c.yi0 = yo0 - 2 * R;
+    c.eps = a.eps;
+#pragma unroll
+    for (int q = 0; q < 13; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c.c[q][j] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c.sa[q][j] = 0.f; c.va[q][j] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c.oI[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c.oP[j] = 0.f;
+    (void)VL;
+    const int steps = (yo1 - yo0) + 4 * R;
+    if (c.mirror) {
+        gf_c4_load_row<R, true>(c, c.yi0, c.nI, c.nP);
+        gf_c4_band<R, true>(c, steps);
+    } else {
+        gf_c4_load_row<R, false>(c, c.yi0, c.nI, c.nP);
+        gf_c4_band<R, false>(c, steps);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+#ifndef GF_NO_HOST   // (stand-alone SASS builds of one kernel define GF_NO_HOST)
+template <int R>
+static const char* gf_c4_launch(const Job& j)
+{
+    using G = GfC4Geom<R>;
+    int sms = 148, mj = 0, mn = 0;
+    gf_rt_device_info(&sms, &mj, &mn);
+    GfWpArgs a;
+    a.guide = j.guide.ptr; a.src = j.src.ptr; a.dst = const_cast<float*>(j.dst.ptr);
+    a.A = nullptr; a.B = nullptr;
+    a.gs = j.guide.stride; a.ss = j.src.stride; a.ds = j.dst.stride; a.abs_ = 0;
+    a.gfs = j.guide.frame_stride; a.sfs = j.src.frame_stride; a.dfs = j.dst.frame_stride; a.abfs = 0;
+    a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
+    a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
+    a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
+    const size_t smem = G::ring_bytes;
+    constexpr int FIT = (int)((size_t)228 * 1024 / (G::ring_bytes + 1024));
+    constexpr int MINB = FIT > 8 ? 8 : (FIT < 1 ? 1 : FIT);
+    int warps_sm = MINB;
+    if (const char* e = getenv("GF_C4_WARPS_PER_SM")) warps_sm = atoi(e);
+    const long target = (long)sms * warps_sm;
+    long nb = target / ((long)a.nstrips * j.count);
+    if (nb < 1) nb = 1;
+    int hb = (int)((j.out_rows + nb - 1) / nb);
+    int hb_min = 2 * R + 8, hb_max = 270;       // measured on 32 x 1080p r=16: 270 -> 2.05 ms, 540 -> 2.28 ms
+    if (const char* e = getenv("GF_C4_HB")) hb = atoi(e);
+    if (hb < hb_min) hb = hb_min;
+    if (hb > hb_max) hb = hb_max;
+    if (hb > j.out_rows) hb = j.out_rows;
+    a.hb = hb;
+    a.nbands = (j.out_rows + hb - 1) / hb;
+    const long items = (long)a.nstrips * a.nbands * j.count;
+    dim3 grid((unsigned)items), block(32);
+    auto k = gf_c4_color_kernel<R, MINB>;
+    if (const char* e = gf_rt_set_smem(k, smem)) return e;
+    GF_LAUNCH(k, grid, block, smem, j.stream, a);
+    return gf_rt_launch_error();
+}
+
+static const char* gf_c4_try(const Job& j, bool* done, const char** name)
+{
+    *done = false;
+    if (!j.color || j.border != GF_REFLECT101 || j.A.ptr) return nullptr;
+    if (getenv("GF_DISABLE_C4") || getenv("GF_DISABLE_FAST")) return nullptr;
+    if (j.guide.channels != 3 || j.guide.coff != 0 || j.src.channels != 1 || j.src.coff != 0 || j.dst.channels != 1 || j.dst.coff != 0)
+        return nullptr;
+    const Plane* pl[3] = {&j.guide, &j.src, &j.dst};
+    for (int i = 0; i < 3; ++i)
+        if ((pl[i]->stride & 3) || (pl[i]->frame_stride & 3) || ((uintptr_t)pl[i]->ptr & 15)) return nullptr;
+    if ((j.width & 3) || j.width < 128 || j.height < 4 * j.r + 2) return nullptr;
+    if ((int64_t)j.buf_rows * j.guide.stride >= (1ll << 31) || (int64_t)j.out_rows * j.dst.stride >= (1ll << 31)) return nullptr;
+    switch (j.r) {
+    case 4: *done = true; *name = "c4_r4"; return gf_c4_launch<4>(j);
+    case 8: *done = true; *name = "c4_r8"; return gf_c4_launch<8>(j);
+    case 12: *done = true; *name = "c4_r12"; return gf_c4_launch<12>(j);
+    case 16: *done = true; *name = "c4_r16"; return gf_c4_launch<16>(j);
+    default: return nullptr;
+    }
+}
+#endif  // GF_NO_HOST

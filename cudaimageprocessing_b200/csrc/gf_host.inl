@@ -82,6 +82,7 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
     float *dI = P.dev, *dP = P.dev + P.cap, *dQ = P.dev + 2 * P.cap;
     int nb = height / (4 * r + 64);
     nb = nb < 1 ? 1 : (nb > 8 ? 8 : nb);
+    if (const char* e = getenv("GF_HOST_BANDS")) { nb = atoi(e); nb = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb); }
     int up_to = 0;
     for (int b = 0; b < nb; ++b) {
         const int y0 = (int)((int64_t)height * b / nb), y1 = (int)((int64_t)height * (b + 1) / nb);

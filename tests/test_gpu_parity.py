@@ -122,10 +122,24 @@ def test_color_1080p_r16(be, border):
     I3 = np.random.default_rng(100).random((1080, 1920, 3), dtype=np.float32)
     p = np.random.default_rng(10000).random((1080, 1920), dtype=np.float32)
     q = be.guided_color(I3, p, 16, 1e-2, border)
+    assert be.api.last_kernel() == ("c4_r16" if border == 0 else "generic_color")
     ref = C.guided_color_f32(I3, p, 16, 1e-2, border, NT)
     err = np.abs(q - ref).max()
     print(f"colour 1080p r=16 border={border}: max err {err:.3e}")
     assert err <= TOL
+
+
+@pytest.mark.parametrize("r", [4, 8, 12, 16])
+def test_color_c4_radii_and_batch(be, r):
+    """The tuned colour-guide kernel (gf_c4.cuh) at every radius it is built for, on a batch of
+    frames whose width is not a multiple of the strip width (border strips on both edges)."""
+    rng = np.random.default_rng(60 + r)
+    I = rng.random((3, 200, 388, 3), dtype=np.float32)
+    p = rng.random((3, 200, 388), dtype=np.float32)
+    q = be.batch(I, p, r, 1e-2, 0)
+    assert be.api.last_kernel() == f"c4_r{r}"
+    for k in range(3):
+        assert np.abs(q[k] - C.guided_color_f32(I[k], p[k], r, 1e-2, 0, NT)).max() <= TOL
 
 
 def test_color_small_and_3ch_src(be):

@@ -233,3 +233,27 @@ def test_gray_s8_batch_strip_kat(be):
     assert be.api.last_kernel() == "s8_r7"
     d = O.to_u8(q)[:32, :44].astype(int) - crop["gold"][:32, :44].astype(int)
     assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 2
+
+
+# ---- the tuned colour-guide kernel (gf_c4.cuh) under the emulator --------------------------------
+@pytest.mark.parametrize("shape,r", [((40, 160), 4), ((50, 256), 8), ((60, 132), 12), ((80, 192), 16)])
+def test_color_c4(be, shape, r, monkeypatch):
+    """interior strips, border strips (mirror shuffles on both image edges), several bands."""
+    monkeypatch.setenv("GF_C4_HB", str(2 * r + 9))
+    h, w = shape
+    rng = np.random.default_rng(40 + r)
+    I3 = rng.random((h, w, 3), dtype=np.float32)
+    p = rng.random((h, w), dtype=np.float32)
+    q = be.guided_color(I3, p, r, 1e-2, 0)
+    assert be.api.last_kernel() == f"c4_r{r}"
+    assert np.abs(q - O.guided_filter_color(I3, p, r, 1e-2, 0)).max() <= TOL
+
+
+def test_color_c4_batch(be):
+    rng = np.random.default_rng(8)
+    I = rng.random((2, 40, 160, 3), dtype=np.float32)
+    p = rng.random((2, 40, 160), dtype=np.float32)
+    q = be.batch(I, p, 8, 1e-2, 0)
+    assert be.api.last_kernel() == "c4_r8"
+    for k in range(2):
+        assert np.abs(q[k] - O.guided_filter_color(I[k], p[k], 8, 1e-2, 0)).max() <= TOL
