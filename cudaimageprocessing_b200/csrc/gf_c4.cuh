@@ -347,14 +347,9 @@ static const char* gf_c4_launch(const Job& j)
     constexpr int MINB = FIT > 8 ? 8 : (FIT < 1 ? 1 : FIT);
     int warps_sm = MINB;
     if (const char* e = getenv("GF_C4_WARPS_PER_SM")) warps_sm = atoi(e);
-    const long target = (long)sms * warps_sm;
-    long nb = target / ((long)a.nstrips * j.count);
-    if (nb < 1) nb = 1;
-    int hb = (int)((j.out_rows + nb - 1) / nb);
-    int hb_min = 2 * R + 8, hb_max = 270;       // measured on 32 x 1080p r=16: 270 -> 2.05 ms, 540 -> 2.28 ms
+    int hb = gf_pick_band_rows(j.out_rows, R, (long)a.nstrips * j.count, (long)sms * warps_sm, 2 * R + 8);
     if (const char* e = getenv("GF_C4_HB")) hb = atoi(e);
-    if (hb < hb_min) hb = hb_min;
-    if (hb > hb_max) hb = hb_max;
+    if (hb < 1) hb = 1;
     if (hb > j.out_rows) hb = j.out_rows;
     a.hb = hb;
     a.nbands = (j.out_rows + hb - 1) / hb;

@@ -97,6 +97,51 @@ def filter_strip(api, I_buf: torch.Tensor, p_buf: torch.Tensor, q_out: torch.Ten
              ctypes.c_void_p(stream) if stream else None)
 
 
+_SIDE_STREAMS = {}
+
+
+def filter_strip_overlapped(api, I_buf: torch.Tensor, p_buf: torch.Tensor, q_out: torch.Tensor, height: int, rank: int,
+                            world: int, r: int, eps: float, border: int, group=None) -> None:
+    """Halo exchange + filter of this rank's strip with the exchange HIDDEN behind compute:
+    the 2r halo rows travel on a side stream (NCCL send/recv over NVLink) while the current stream
+    already filters the interior rows, whose 4r+1-row neighbourhood lies inside the rank's own rows;
+    the two 2r-row seam bands are filtered once the halos have landed.  I_buf/p_buf come from
+    alloc_strip with the rank's rows filled in; q_out holds the rank's own rows."""
+    y0, y1 = strip_rows(height, rank, world)
+    top, bot = halo_rows(height, rank, world, r)
+    w = I_buf.shape[1]
+    cuda = I_buf.is_cuda
+    main = landed = None
+    if cuda:
+        main = torch.cuda.current_stream()
+        dev = I_buf.device.index
+        side = _SIDE_STREAMS.get(dev)
+        if side is None:
+            side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=I_buf.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            exchange_halos_inplace([I_buf, p_buf], height, rank, world, r, group)
+            landed = torch.cuda.Event()
+            landed.record(side)
+    else:                              # host tensors (gloo tests): same row ranges, no overlap to be had
+        exchange_halos_inplace([I_buf, p_buf], height, rank, world, r, group)
+
+    def run(a, b):
+        if b > a:
+            api.call("gf_guided_gray_strip", I_buf.data_ptr(), p_buf.data_ptr(), q_out[a - y0:].data_ptr(), w, height, y0 - top,
+                     I_buf.shape[0], a, b - a, I_buf.stride(0), p_buf.stride(0), q_out.stride(0), r, eps, border,
+                     ctypes.c_void_p(main.cuda_stream) if cuda else None)
+    lo = min(y1, y0 + 2 * r) if top else y0
+    hi = max(lo, y1 - 2 * r) if bot else y1
+    run(lo, hi)                       # interior: needs no halo row
+    if cuda:
+        main.wait_event(landed)
+    run(y0, lo)                       # seam bands
+    run(hi, y1)
+
+
 def filter_frames(api, I: torch.Tensor, p: torch.Tensor, q: torch.Tensor, r: int, eps: float, border: int,
                   stream: Optional[int] = None) -> None:
     """Filters this rank's block of frames with ONE launch.  I: [n,h,w] (gray) or [n,h,w,3]

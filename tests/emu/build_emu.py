@@ -16,7 +16,7 @@ def build_emu(force: bool = False) -> str:
            [os.path.join(ROOT, "include", "gf_b200.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
-    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-DGF_CPU_EMU",
+    cmd = ["/usr/bin/g++", "-O1", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-DGF_CPU_EMU",
            "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            "-x", "c++", os.path.join(CSRC, "gf_api.cu"), os.path.join(HERE, "cuda_emu.cpp"), "-o", LIB]
     if os.path.exists(os.path.join(CSRC, "gf_fast.cuh")):

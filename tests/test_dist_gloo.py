@@ -51,6 +51,13 @@ def _worker(rank, world, port, H, W, r, border, out_dir):
         q = torch.empty((y1 - y0, W), dtype=torch.float32)
         D.filter_strip(be.api, bufI, bufP, q, H, rank, world, r, 1e-2, border)
         np.save(os.path.join(out_dir, f"q_{rank}.npy"), q.numpy())
+        # the overlapped form (interior rows first, seam bands after the halos) gives the same strip
+        bufI2, viewI2 = D.alloc_strip(H, W, rank, world, r, "cpu")
+        bufP2, viewP2 = D.alloc_strip(H, W, rank, world, r, "cpu")
+        viewI2.copy_(torch.from_numpy(I[y0:y1])); viewP2.copy_(torch.from_numpy(p[y0:y1]))
+        q2 = torch.full((y1 - y0, W), float("nan"), dtype=torch.float32)
+        D.filter_strip_overlapped(be.api, bufI2, bufP2, q2, H, rank, world, r, 1e-2, border)
+        assert np.abs(q2.numpy() - q.numpy()).max() <= 2e-6
         # batch sharding covers every frame exactly once
         spans = [D.shard_frames(11, k, world) for k in range(world)]
         assert spans[0][0] == 0 and spans[-1][1] == 11 and all(spans[k][1] == spans[k + 1][0] for k in range(world - 1))

@@ -129,6 +129,22 @@ def test_color_1080p_r16(be, border):
     assert err <= TOL
 
 
+def test_long_bands_do_not_drift(be, monkeypatch):
+    """Large batches / tall strips make the band chooser pick full-height bands: the running sums
+    then run for the whole image (colour: no re-seed; gray: re-seeded every 2r+1 rows)."""
+    I3 = np.random.default_rng(100).random((1080, 1920, 3), dtype=np.float32)
+    p = np.random.default_rng(10000).random((1080, 1920), dtype=np.float32)
+    monkeypatch.setenv("GF_C4_HB", "1080")
+    q = be.guided_color(I3, p, 16, 1e-2, 0)
+    assert be.api.last_kernel() == "c4_r16"
+    assert np.abs(q - C.guided_color_f32(I3, p, 16, 1e-2, 0, NT)).max() <= 2e-5
+    I, p = synth_pair(2160, 3840, seed=0)
+    monkeypatch.setenv("GF_S8_HB", "2160")
+    q = be.guided_gray(I, p, 8, 1e-2, 0)
+    assert be.api.last_kernel() == "s8_r8"
+    assert np.abs(q - C.guided_gray_f64(I, p, 8, 1e-2, 0, NT)).max() <= 2e-6
+
+
 @pytest.mark.parametrize("r", [4, 8, 12, 16])
 def test_color_c4_radii_and_batch(be, r):
     """The tuned colour-guide kernel (gf_c4.cuh) at every radius it is built for, on a batch of
