@@ -175,6 +175,23 @@ def reference_gpu_numbers(torch, frames):
             torch.cuda.synchronize()
             out[name] = (time.perf_counter() - t0) / n * 1e3
         ref.gfref_destroy(g)
+        # the same two calls through OUR drop-in surface, timed the same way
+        import cudaimageprocessing_b200 as pkg
+        api = pkg.api()
+        hnd = ctypes.c_void_p()
+        api.call("gf_create", ctypes.addressof(hnd), W, H, 1, 1)
+        for name, fn, n in (("ours_class_run_r8_ms", lambda: api.call("gf_run", hnd, dI.data_ptr(), dp.data_ptr(), dq.data_ptr(), 8, EPS,
+                                                                        pkg.BORDER_TRUNCATE, 0, 0, 0, None), 20),
+                            ("ours_hguided_r7_ms", lambda: api.call("gf_guided_gray", dI.data_ptr(), dp.data_ptr(), dq.data_ptr(), None, None,
+                                                                    W, H, 0, 0, 0, 0, 7, EPS, pkg.BORDER_REFLECT101, None), 20)):
+            fn(); fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            out[name] = (time.perf_counter() - t0) / n * 1e3
+        api.call("gf_destroy", hnd)
         out["note"] = ("reference CUDA sources compiled unmodified for sm_100a, launched on the legacy default stream; "
                        "wall clock around n synchronised calls")
         return out

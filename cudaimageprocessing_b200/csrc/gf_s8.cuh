@@ -189,6 +189,8 @@ struct GfS8Ctx {
     GfS8Edge edge;                                   // MODE 1 only
     bool out_l, out_r;                               // MODE 3 only: lane lies left / right of the image
     int vofs, sofs;                                  // MODE 3 only: vector / scalar source offsets relative to x0
+    bool lane_in;                                    // MODE 4 only: this lane's 8 columns lie inside the image
+    float2 cx[4];                                    // MODE 4 only: in-image columns in the window [x-R, x+R] of each column
     int sx[8];                                       // XMAP only: source column of each of the 8 columns, relative to x0
     float eps;
     GfNorm nk;                                       // 1 / (2R+1)^2
@@ -220,7 +222,9 @@ __device__ __forceinline__ float gf_s8_rcp(float d)
 // Strip modes: 0 interior; 1 analytic REFLECT101 image edges (R = 8); 3 mirror loads -- REFLECT101,
 // width % 8 == 0: a lane that lies outside the image reads the aligned 8-column group that holds
 // 7 of its 8 mirror columns plus one scalar, and permutes at compile time (no per-column gather);
-// 2 generic per-column border map (any border, any width; slow, rarely needed).
+// 2 generic per-column border map (any border, any width; slow, rarely needed); 4 TRUNCATE border
+// (the class API): pixels outside the image contribute nothing and every mean divides by the number of
+// in-image pixels of its window (guided_filter_d.cu:251-262) -- zero-filled loads, per-pixel counts.
 template <int MODE, int R>
 __device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R>& c, const float* rowp, float2 (&v)[4])
 {
@@ -240,12 +244,50 @@ __device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R>& c, const float* rowp,
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = make_float2(d[2 * i], d[2 * i + 1]);
+    } else if (MODE == 4) {
+        if (c.lane_in) {
+            gf_ld8(rowp, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = make_float2(0.f, 0.f);
+        }
     } else if (MODE != 2 || c.vec_ok) {
         gf_ld8(rowp, v);
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = make_float2(rowp[c.sx[2 * i]], rowp[c.sx[2 * i + 1]]);
     }
+}
+
+// Row y (any integer) of both planes: REFLECT borders map the row index; MODE 4 (TRUNCATE) rows outside
+// the image are zeros.
+template <int MODE, int R>
+__device__ __forceinline__ void gf_s8_ld_row(const GfS8Ctx<R>& c, int y, float2 (&vI)[4], float2 (&vP)[4])
+{
+    if (MODE == 4) {
+        if (y < 0 || y > c.buf_ylast) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { vI[i] = make_float2(0.f, 0.f); vP[i] = make_float2(0.f, 0.f); }
+            return;
+        }
+        const int o = y - c.buf_y0;
+        gf_s8_ld<MODE>(c, c.gI + o * c.gs, vI);
+        gf_s8_ld<MODE>(c, c.gP + o * c.ss, vP);
+    } else {
+        int rn = gf_s8_map_y(y, c.height, c.border);
+        rn = rn > c.buf_ylast ? c.buf_ylast : rn;
+        const int o = rn - c.buf_y0;
+        gf_s8_ld<MODE>(c, c.gI + o * c.gs, vI);
+        gf_s8_ld<MODE>(c, c.gP + o * c.ss, vP);
+    }
+}
+
+// TRUNCATE: number of image rows in [y-R, y+R]
+template <int R>
+__device__ __forceinline__ float gf_s8_cnt_y(int y, int height)
+{
+    const int lo = y - R < 0 ? 0 : y - R, hi = y + R > height - 1 ? height - 1 : y + R;
+    return (float)(hi - lo + 1 > 0 ? hi - lo + 1 : 1);
 }
 
 // c = f, f = 0: f holds exactly the rows of the current window, summed without a subtraction
@@ -305,14 +347,8 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
     }
     // rows of the next iteration, consumed at the top of it
     if (!(GF_S8_ABL & 4)) {
-        int rn = gf_s8_map_y(yi + 1, c.height, c.border);
-        rn = rn > c.buf_ylast ? c.buf_ylast : rn;
-        const int on = rn - c.buf_y0;
-        gf_s8_ld<MODE>(c, c.gI + on * c.gs, c.nI);
-        gf_s8_ld<MODE>(c, c.gP + on * c.ss, c.nP);
-        const int oo = gf_s8_map_y(yi + 1 - KW, c.height, c.border) - c.buf_y0;
-        gf_s8_ld<MODE>(c, c.gI + oo * c.gs, c.oI);
-        gf_s8_ld<MODE>(c, c.gP + oo * c.ss, c.oP);
+        gf_s8_ld_row<MODE>(c, yi + 1, c.nI, c.nP);
+        gf_s8_ld_row<MODE>(c, yi + 1 - KW, c.oI, c.oP);
         if (GF_S8_PF > 0 && MODE <= 1 && lane < 8) {
             // L2 prefetch hint a few rows ahead: 8 lanes x one 128-byte line = the warp's 256 columns.
             // (Measured: +3% over no hint; a hint per 32-byte sector from all 32 lanes is 10% SLOWER.)
@@ -351,11 +387,22 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
         if (full) {                                     // q of row yo = yi-1-2R; its guide row is oI
             const int yo = yi - 1 - 2 * R;
             float2 q[4];
-            const float2 nh = gf_dup2(c.nk.hi), nl = gf_dup2(c.nk.lo);
+            if (MODE == 4) {                           // mean over the in-image part of the window of (x, yo)
+                const float2 cy = gf_dup2(gf_s8_cnt_y<R>(yo, c.height));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 v = gf_fma2(c.sA[i], gI[i], c.sB[i]);
-                q[i] = gf_fma2(v, nh, gf_mul2(v, nl));
+                for (int i = 0; i < 4; ++i) {
+                    const float2 n2 = gf_mul2(c.cx[i], cy);
+                    float2 rn = make_float2(gf_s8_rcp(n2.x), gf_s8_rcp(n2.y));
+                    rn = gf_fma2(gf_fma2(gf_neg2(n2), rn, gf_dup2(1.0f)), rn, rn);
+                    q[i] = gf_mul2(gf_fma2(c.sA[i], gI[i], c.sB[i]), rn);
+                }
+            } else {
+                const float2 nh = gf_dup2(c.nk.hi), nl = gf_dup2(c.nk.lo);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 v = gf_fma2(c.sA[i], gI[i], c.sB[i]);
+                    q[i] = gf_fma2(v, nh, gf_mul2(v, nl));
+                }
             }
             float* pq = c.gQ + (yo - c.out_y0) * c.ds;
             if (c.out_lane && !(GF_S8_ABL & 8)) {
@@ -381,6 +428,27 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
         gf_s8_window<R, EDGE>(c.cP, hP, lane, c.edge);
         gf_s8_window<R, EDGE>(c.cIP, hIP, lane, c.edge);
         gf_s8_window<R, EDGE>(c.cII, hII, lane, c.edge);
+        if (MODE == 4) {
+            // TRUNCATE: N = (in-image columns) x (in-image rows) of the window of (x, yc); a, b are zero outside the image
+            const int yc = yi - R;
+            const bool ok = c.lane_in && yc >= 0 && yc < c.height;
+            const float2 cy = gf_dup2(gf_s8_cnt_y<R>(yc, c.height));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 n2 = gf_mul2(c.cx[i], cy), mn2 = gf_neg2(n2);
+                const float2 nnum = gf_fma2(hI[i], hP[i], gf_mul2(hIP[i], mn2));
+                const float2 nden = gf_fma2(hI[i], hI[i], gf_fma2(hII[i], mn2, gf_mul2(gf_mul2(n2, n2), gf_dup2(-c.eps))));
+                float2 rc = make_float2(gf_s8_rcp(nden.x), gf_s8_rcp(nden.y));
+                rc = gf_fma2(gf_fma2(gf_neg2(nden), rc, gf_dup2(1.0f)), rc, rc);
+                float2 rn = make_float2(gf_s8_rcp(n2.x), gf_s8_rcp(n2.y));
+                rn = gf_fma2(gf_fma2(mn2, rn, gf_dup2(1.0f)), rn, rn);
+                const float2 aa = gf_mul2(nnum, rc);
+                const float2 bb = gf_mul2(gf_fma2(gf_neg2(aa), hI[i], hP[i]), rn);
+                c.va[i] = ok ? aa : make_float2(0.f, 0.f);
+                c.vb[i] = ok ? bb : make_float2(0.f, 0.f);
+            }
+            return;
+        }
         const float N = (float)(KW * KW);
         const float2 mN = gf_dup2(-N), mE = gf_dup2(-c.eps * N * N);
         const float2 nh = gf_dup2(c.nk.hi), nl = gf_dup2(c.nk.lo);
@@ -414,11 +482,7 @@ __device__ __forceinline__ void gf_s8_warmup(GfS8Ctx<R>& c)
         // rows t0+1 .. t0+CH  (row t0 is already in nI/nP)
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
-            int rn = gf_s8_map_y(c.yi0 + t0 + 1 + k, c.height, c.border);
-            rn = rn > c.buf_ylast ? c.buf_ylast : rn;
-            const int on = rn - c.buf_y0;
-            gf_s8_ld<MODE>(c, c.gI + on * c.gs, bI[k]);
-            gf_s8_ld<MODE>(c, c.gP + on * c.ss, bP[k]);
+            gf_s8_ld_row<MODE>(c, c.yi0 + t0 + 1 + k, bI[k], bP[k]);
         }
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
@@ -485,6 +549,11 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
         mode = 1;
         if (first) { xl = 0; lane_lo = 0; }
         if (last && !first) { xl = a.width - G::WIN; lane_lo = 4 * H1; col_min = strip * G::WOUT; }
+    } else if (a.border == GF_TRUNCATE) {
+        // interior warps (every window they touch is full) run the plain code; the others count pixels
+        const int by0 = a.out_y0 + band * a.hb, by1 = min(a.out_y0 + a.out_rows, by0 + a.hb);
+        const bool inside = xl >= 0 && xl + G::WIN <= a.width && by0 - 2 * R >= 0 && by1 + 2 * R <= a.height;
+        mode = inside ? 0 : 4;
     } else if (xl < 0 || xl + G::WIN > a.width) {
         mode = (a.border == GF_REFLECT101 && (a.width & 7) == 0 && a.width >= G::WIN) ? 3 : 2;
     }
@@ -502,6 +571,10 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
         c.buf_ylast = yl < a.height - 1 ? yl : a.height - 1;
     }
     c.vec_ok = c.x0 >= 0 && c.x0 + 7 < a.width;
+    c.lane_in = c.vec_ok;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        c.cx[i] = make_float2(gf_count(c.x0 + 2 * i, a.width, R, GF_TRUNCATE), gf_count(c.x0 + 2 * i + 1, a.width, R, GF_TRUNCATE));
     c.out_l = mode == 3 && c.x0 < 0;
     c.out_r = mode == 3 && c.x0 >= a.width;
     c.vofs = c.out_l ? -2 * c.x0 - 8 : (c.out_r ? 2 * a.width - 8 - 2 * c.x0 : 0);
@@ -528,6 +601,9 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
     } else if (mode == 3) {
         gf_s8_ld<3>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<3>(c, c.gP + o0 * c.ss, c.nP);
         gf_s8_band<R, 3>(c, steps);
+    } else if (mode == 4) {
+        gf_s8_ld_row<4>(c, c.yi0, c.nI, c.nP);
+        gf_s8_band<R, 4>(c, steps);
     } else {
         gf_s8_ld<0>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<0>(c, c.gP + o0 * c.ss, c.nP);
         if constexpr (R == 8) {
@@ -604,7 +680,8 @@ static const char* gf_s8_launch(const Job& j)
 static const char* gf_s8_try(const Job& j, bool* done, const char** name)
 {
     *done = false;
-    if (j.color || j.border == GF_TRUNCATE || j.A.ptr) return nullptr;
+    if (j.color || j.A.ptr) return nullptr;
+    if (j.border == GF_TRUNCATE && ((j.width & 7) || j.width < 256)) return nullptr;
     if (getenv("GF_DISABLE_S8") || getenv("GF_DISABLE_FAST")) return nullptr;
     const Plane* pl[3] = {&j.guide, &j.src, &j.dst};
     for (int i = 0; i < 3; ++i)

@@ -198,10 +198,13 @@ def test_gray_wp_k8(be, shape, r, border, monkeypatch):
 # ---- the headline kernel (gf_s8.cuh: 8 columns per lane) under the emulator ----------------------
 @pytest.mark.parametrize("shape,r,border", [((60, 700), 8, 0), ((75, 512), 8, 2), ((64, 256), 8, 0), ((50, 480), 8, 0), ((45, 472), 8, 0), ((40, 224), 8, 0), ((90, 1000), 8, 0),
                                             ((50, 264), 7, 0), ((70, 520), 7, 2), ((30, 300), 4, 0), ((40, 320), 4, 0), ((100, 640), 16, 0), ((140, 512), 32, 0),
-                                            ((140, 456), 16, 2)])
+                                            ((140, 456), 16, 2), ((75, 512), 8, 1), ((50, 264), 7, 1), ((100, 640), 16, 1),
+                                            ((40, 320), 4, 1), ((180, 1000), 8, 1)])
 def test_gray_s8(be, shape, r, border, monkeypatch):
-    """interior and border strips (mapped loads), several bands (GF_S8_HB), a width that is not a
-    multiple of 8 (partial last lane), heights that end inside / right after a re-seed period."""
+    """interior and border strips (analytic edges, mirror loads, mapped loads, TRUNCATE counts),
+    several bands (GF_S8_HB), a width that is not a multiple of 8 (partial last lane), heights that
+    end inside / right after a re-seed period; the last case has warps that are interior in a
+    TRUNCATE job (plain code) next to clipped ones."""
     monkeypatch.setenv("GF_S8_HB", str(2 * r + 9))
     I, p = synth_pair(*shape, seed=71, kind="structured")
     w = shape[1]
