@@ -229,17 +229,23 @@ template <int R, bool MIRROR>
 __device__ __forceinline__ void gf_c4_band(GfC4Ctx<R>& c, int steps)
 {
     constexpr int KW = 2 * R + 1;
-    // warm-up rows t in [0, 2R): vertical accumulation only, two rows in flight
+    // warm-up rows t in [0, 2R): vertical accumulation only; rows are loaded four at a time so that
+    // the band start costs 2R/4 DRAM latencies instead of 2R (2R is a multiple of 4: R % 4 == 0)
     {
-        float bI[12], bP[4];
+        float bI[4][12], bP[4][4];
 #pragma unroll 1
-        for (int t = 0; t < 2 * R; t += 2) {
-            gf_c4_load_row<R, MIRROR>(c, c.yi0 + t + 1, bI, bP);
+        for (int t = 0; t < 2 * R; t += 4) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gf_c4_accum<false>(c.c, j, c.nI[3 * j], c.nI[3 * j + 1], c.nI[3 * j + 2], c.nP[j]);
-            gf_c4_load_row<R, MIRROR>(c, c.yi0 + t + 2, c.nI, c.nP);
+            for (int k = 0; k < 4; ++k) gf_c4_load_row<R, MIRROR>(c, c.yi0 + t + 1 + k, bI[k], bP[k]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gf_c4_accum<false>(c.c, j, bI[3 * j], bI[3 * j + 1], bI[3 * j + 2], bP[j]);
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gf_c4_accum<false>(c.c, j, c.nI[3 * j], c.nI[3 * j + 1], c.nI[3 * j + 2], c.nP[j]);
+#pragma unroll
+                for (int i = 0; i < 12; ++i) c.nI[i] = bI[k][i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c.nP[j] = bP[k][j];
+            }
         }
     }
     int t = 2 * R;

@@ -130,6 +130,47 @@ def test_color_1080p_r16(be, border):
     assert err <= TOL
 
 
+def test_no_out_of_bounds_access(be):
+    """(compute-sanitizer is closed on this pool.)  Every plane sits inside a larger allocation whose
+    guard rows and row padding are NaN: a read outside the image poisons q, a write outside the
+    image destroys a guard NaN.  Shapes walk through every strip mode of the s8 and c4 kernels."""
+    import torch
+    G = 3
+
+    def guarded(h, s, fill=None):
+        big = torch.full((h + 2 * G, s), float("nan"), device="cuda")
+        if fill is not None:
+            big[G:G + h, :fill.shape[1]] = fill
+        return big, big[G:G + h]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for (h, w) in [(70, 64), (70, 72), (90, 256), (90, 264), (150, 480), (140, 1000), (135, 1004)]:
+        for r in (1, 4, 7, 8, 16, 32):
+            if h < 4 * r + 2:
+                continue
+            for border in (0, 1, 2):
+                s_ = (w + 7) // 8 * 8 + 8                       # 8 floats of NaN padding after every row
+                bI, vI = guarded(h, s_, torch.rand((h, w), device="cuda", generator=g))
+                bP, vP = guarded(h, s_, torch.rand((h, w), device="cuda", generator=g))
+                bQ, vQ = guarded(h, s_)
+                be.api.call("gf_guided_gray", vI.data_ptr(), vP.data_ptr(), vQ.data_ptr(), None, None, w, h, s_, s_, s_, 0,
+                            r, 1e-2, border, None)
+                torch.cuda.synchronize()
+                assert torch.isfinite(vQ[:, :w]).all(), (h, w, r, border, be.api.last_kernel())
+                assert torch.isnan(vQ[:, w:]).all() and torch.isnan(bQ[:G]).all() and torch.isnan(bQ[G + h:]).all(), \
+                    (h, w, r, border, be.api.last_kernel())
+    for (h, w) in [(70, 128), (70, 132), (80, 256), (90, 388)]:
+        for r in (4, 8, 12, 16):
+            if h < 4 * r + 2:
+                continue
+            bI, vI = guarded(h, 3 * w + 12, torch.rand((h, 3 * w), device="cuda", generator=g))
+            bP, vP = guarded(h, w + 4, torch.rand((h, w), device="cuda", generator=g))
+            bQ, vQ = guarded(h, w + 4)
+            be.api.call("gf_guided_color", vI.data_ptr(), vP.data_ptr(), vQ.data_ptr(), w, h, 1, 3 * w + 12, w + 4, w + 4, r, 1e-2, 0, None)
+            torch.cuda.synchronize()
+            assert torch.isfinite(vQ[:, :w]).all(), (h, w, r, be.api.last_kernel())
+            assert torch.isnan(vQ[:, w:]).all() and torch.isnan(bQ[:G]).all() and torch.isnan(bQ[G + h:]).all(), (h, w, r)
+
+
 def test_long_bands_do_not_drift(be, monkeypatch):
     """Large batches / tall strips make the band chooser pick full-height bands: the running sums
     then run for the whole image (colour: no re-seed; gray: re-seeded every 2r+1 rows)."""
