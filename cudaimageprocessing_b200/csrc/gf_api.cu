@@ -14,6 +14,7 @@
 #include "gf_generic.cuh"
 #include "gf_job.h"
 #include "gf_pointwise.cuh"
+#include "gf_integral.cuh"
 #include "gf_rt.h"
 #ifdef GF_HAVE_FAST
 #include "gf_fast.cuh"
@@ -234,10 +235,43 @@ struct gf_filter {
     int width, height, gch, sch;
 };
 
+
+template <class T>
+static int integral_entry(const unsigned char* src, T* integral, T* scratch, int sw, int sh, int w, int h, int64_t ss, int64_t ds,
+                          void* stream, const char* name)
+{
+    if (!src || !integral) return fail(GF_ERR_INVALID, "%s: null pointer", name);
+    if (sw <= 0 || sh <= 0 || w < sw || h < sh) return fail(GF_ERR_INVALID, "%s: bad size %dx%d -> %dx%d", name, sw, sh, w, h);
+    if (ss <= 0) ss = sw;
+    if (ds <= 0) ds = w;
+    if (ss < sw || ds < w) return fail(GF_ERR_INVALID, "%s: row stride smaller than a row", name);
+    if (const char* e = gf_sat_launch<T>(src, integral, scratch, sw, sh, w, h, ss, ds, stream)) return fail(GF_ERR_CUDA, "%s: %s", name, e);
+    g_launches += 3;
+    g_kernel = sizeof(T) == 4 ? "integral_i32" : "integral_i64";
+    return GF_OK;
+}
+
 extern "C" {
 
 const char* gf_last_error(void) { return g_err.c_str(); }
 int gf_version(void) { return 100; }
+int gf_integral_u8_i32(const unsigned char* src, int32_t* integral, int32_t* scratch, int width, int height, int64_t src_stride,
+                       int64_t dst_stride, void* stream)
+{
+    return integral_entry<int32_t>(src, integral, scratch, width, height, width, height, src_stride, dst_stride, stream, "gf_integral_u8_i32");
+}
+int gf_integral_u8_i64(const unsigned char* src, int64_t* integral, int64_t* scratch, int width, int height, int64_t src_stride,
+                       int64_t dst_stride, void* stream)
+{
+    return integral_entry<int64_t>(src, integral, scratch, width, height, width, height, src_stride, dst_stride, stream, "gf_integral_u8_i64");
+}
+int gf_integral_u8_i32_padded(const unsigned char* src, int32_t* integral, int src_width, int src_height, int64_t src_stride,
+                              int dst_width, int dst_height, void* stream)
+{
+    return integral_entry<int32_t>(src, integral, nullptr, src_width, src_height, dst_width, dst_height, src_stride, dst_width, stream,
+                                   "gf_integral_u8_i32_padded");
+}
+
 const char* gf_last_kernel(void) { return g_kernel; }
 int64_t gf_launch_count(void) { return g_launches.load(); }
 

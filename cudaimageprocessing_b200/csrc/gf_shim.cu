@@ -7,6 +7,7 @@
 #include "../../include/gf_b200.h"
 #include "../../include/guided_filter.h"
 #include "../../include/guided_filter_d.h"
+#include "../../include/integral_d.h"
 
 namespace {
 void handle(int rc, const char* where)
@@ -96,4 +97,15 @@ void hGuidedFilter(float* d_guided, float* d_src, float* d_dst, float* d_A, floa
     handle(gf_guided_gray(d_guided, d_src, d_dst, fill_ab ? d_A : nullptr, fill_ab ? d_B : nullptr, width, height, stride, stride,
                           stride, stride, radius, eps, GF_BORDER_REFLECT101, nullptr),
            "hGuidedFilter");
+}
+
+// ---- Integral/ module (Integral/integral_d.h:5-8) ---------------------------------------------------
+void hIntegral(unsigned char* src, int* integral, int* buff, int width, int height, int sstride, int dstride)
+{
+    handle(gf_integral_u8_i32(src, integral, buff, width, height, sstride, dstride, nullptr), "hIntegral");
+}
+
+void hAligned4Integral(unsigned char* src, int* integral, int swidth, int sheight, int sstride, int dwidth, int dheight)
+{
+    handle(gf_integral_u8_i32_padded(src, integral, swidth, sheight, sstride, dwidth, dheight, nullptr), "hAligned4Integral");
 }

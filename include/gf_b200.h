@@ -144,6 +144,21 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
 int gf_host_alloc(void** ptr, size_t bytes);
 int gf_host_free(void* ptr);
 
+/* ---- Integral/ module: summed-area table of a uint8 image ----------------
+   Replace hIntegral / hAligned4Integral (Integral/integral_d.h:5-8, integral_d.cu:863-930):
+   integral[y*dst_stride + x] = sum of src over rows <= y and columns <= x (inclusive, W x H).
+   Strides in ELEMENTS.  The int32 form wraps modulo 2^32 exactly like the reference's int
+   accumulators; the int64 form never overflows (use it above 8.4 Mpix).  `scratch` (optional):
+   at least ceil(height/16) * width elements -- the reference's w*h `buff` is always enough;
+   NULL = stream-ordered temporary.  The padded form writes a dst_width x dst_height table
+   (>= the source size, e.g. aligned to 4) of the zero-extended image. */
+int gf_integral_u8_i32(const unsigned char* src, int32_t* integral, int32_t* scratch, int width, int height,
+                       int64_t src_stride, int64_t dst_stride, void* stream);
+int gf_integral_u8_i64(const unsigned char* src, int64_t* integral, int64_t* scratch, int width, int height,
+                       int64_t src_stride, int64_t dst_stride, void* stream);
+int gf_integral_u8_i32_padded(const unsigned char* src, int32_t* integral, int src_width, int src_height,
+                              int64_t src_stride, int dst_width, int dst_height, void* stream);
+
 /* Which kernel family the last gf_guided_* call on this thread used ("fast_r8", "generic"...)
    and how many kernels it launched; for tests and bench.py's gpu_launches. */
 const char* gf_last_kernel(void);

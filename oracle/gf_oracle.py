@@ -229,3 +229,14 @@ def box_sum_u8(img_u8: np.ndarray, r: int, mode: int) -> np.ndarray:
         return np.moveaxis(c[2 * r + 1: 2 * r + 1 + n] - c[0:n], 0, axis)
 
     return axis_sum(axis_sum(a, 1), 0)
+
+
+# ---- Integral/ module ---------------------------------------------------------
+def integral_u8(img, dtype=np.int64):
+    """Inclusive summed-area table of a uint8 image, W x H (no zero row/column): the layout of the
+    reference's hIntegral (Integral/integral_d.cu:863-893; Integral/main.cpp:124 compares it with
+    cv::integral's [1:, 1:]).  dtype=np.int32 wraps modulo 2^32 like the reference's int accumulators."""
+    sat = np.cumsum(np.cumsum(img.astype(np.int64), axis=0), axis=1)
+    if np.dtype(dtype) == np.int32:
+        return (sat & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
+    return sat.astype(dtype)

@@ -35,6 +35,9 @@ struct dim3 {
 struct float2 { float x, y; };
 struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
 struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
+struct __attribute__((aligned(16))) longlong2 { long long x, y; };
+static inline longlong2 make_longlong2(long long x, long long y) { return longlong2{x, y}; }
 struct int2 { int x, y; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
