@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(32) gf_sat_cols_kernel(const GfSatArgs<T> a)
     for (int j = 0; j < 8; ++j) v[j] = 0;
     const bool full_in = ALIGNED && x0 + 7 < a.sw;       // 8 source bytes, 8-byte aligned
     const bool full_out = ALIGNED && x0 + 7 < a.w;
+#pragma unroll 4
     for (int y = y0; y < y1; ++y) {
         unsigned b[8];
         if (y < a.sh && full_in) {
@@ -111,11 +112,10 @@ __global__ void __launch_bounds__(128) gf_sat_rows_kernel(const GfSatArgs<T> a)
     const T* up = a.aux + (int64_t)(y / a.hb) * a.w;     // carry of the bands above, per column
     T* row = a.out + (int64_t)y * a.ds;
     T carry = 0;
-    for (int xb = 0; xb < a.w; xb += 256) {
+    // chunk loads run one chunk ahead of the scan (the scan of chunk k only needs the carry of chunk k-1)
+    auto load = [&](int xb, T (&v)[8]) {
         const int x0 = xb + 8 * lane;
-        T v[8];
-        const bool full = ALIGNED && x0 + 7 < a.w;
-        if (full) {
+        if (ALIGNED && x0 + 7 < a.w) {
             if (sizeof(T) == 4) {
                 const int4 t0 = reinterpret_cast<const int4*>(row + x0)[0], t1 = reinterpret_cast<const int4*>(row + x0)[1];
                 const int4 u0 = reinterpret_cast<const int4*>(up + x0)[0], u1 = reinterpret_cast<const int4*>(up + x0)[1];
@@ -129,6 +129,16 @@ __global__ void __launch_bounds__(128) gf_sat_rows_kernel(const GfSatArgs<T> a)
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = x0 + j < a.w ? row[x0 + j] + up[x0 + j] : (T)0;
         }
+    };
+    T nv[8];
+    load(0, nv);
+    for (int xb = 0; xb < a.w; xb += 256) {
+        const int x0 = xb + 8 * lane;
+        T v[8];
+        const bool full = ALIGNED && x0 + 7 < a.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = nv[j];
+        if (xb + 256 < a.w) load(xb + 256, nv);
 #pragma unroll
         for (int j = 1; j < 8; ++j) v[j] += v[j - 1];
         T incl = v[7];
