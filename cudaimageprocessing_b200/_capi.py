@@ -31,6 +31,7 @@ SIGNATURES = {
     "gf_guided_gray_host": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int]),
     "gf_host_alloc": (c_int, [P, c_size_t]),
     "gf_host_free": (c_int, [P]),
+    "gf_guided_gray_u8": (c_int, [P, P, P, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_float, c_int, P]),
     "gf_integral_u8_i32": (c_int, [P, P, P, c_int, c_int, c_int64, c_int64, P]),
     "gf_integral_u8_i64": (c_int, [P, P, P, c_int, c_int, c_int64, c_int64, P]),
     "gf_integral_u8_i32_padded": (c_int, [P, P, c_int, c_int, c_int64, c_int, c_int, P]),

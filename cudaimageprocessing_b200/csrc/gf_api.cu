@@ -349,6 +349,35 @@ int gf_guided_gray(const float* guide, const float* src, float* dst, float* A, f
     return run_jobs(&j, 1);
 }
 
+int gf_guided_gray_u8(const unsigned char* guide, const unsigned char* src, unsigned char* dst, int width, int height,
+                      int64_t guide_stride, int64_t src_stride, int64_t dst_stride, int r, float eps, int border, void* stream)
+{
+#ifdef GF_HAVE_FAST
+    Job j;
+    j.width = width; j.height = height; j.buf_rows = height; j.out_rows = height;
+    j.r = r; j.eps = eps; j.border = border; j.stream = stream;
+    // Plane carries float*: the u8 planes are reinterpreted, every stride is in ELEMENTS (= bytes here)
+    j.guide = Plane{reinterpret_cast<const float*>(guide), or_packed(guide_stride, width, 1), 0, 1, 0};
+    j.src = Plane{reinterpret_cast<const float*>(src), or_packed(src_stride, width, 1), 0, 1, 0};
+    j.dst = Plane{reinterpret_cast<const float*>(dst), or_packed(dst_stride, width, 1), 0, 1, 0};
+    j.A = j.B = Plane{nullptr, 0, 0, 1, 0};
+    if (int rc = check_common(j)) return rc;
+    if (dst == guide || dst == src) return fail(GF_ERR_UNSUPPORTED, "gf_guided_gray_u8: in-place filtering is not supported");
+    bool done = false;
+    const char* name = nullptr;
+    const char* e = gf_s8_try(j, &done, &name, true);
+    if (!done)
+        return fail(GF_ERR_UNSUPPORTED, "gf_guided_gray_u8 needs r in {4,7,8,16}, width >= 64, height >= 4r+2, 8-byte aligned rows "
+                                        "(stride %% 8 == 0) and, for the TRUNCATE border, width %% 8 == 0 and >= 256");
+    if (e) return fail(GF_ERR_CUDA, "%s launch: %s", name, e);
+    g_launches++;
+    g_kernel = name;
+    return GF_OK;
+#else
+    return fail(GF_ERR_UNSUPPORTED, "gf_guided_gray_u8: built without the tuned kernels");
+#endif
+}
+
 int gf_guided_color(const float* guide3, const float* src, float* dst, int width, int height, int src_channels,
                     int64_t guide_stride, int64_t src_stride, int64_t dst_stride, int r, float eps, int border, void* stream)
 {

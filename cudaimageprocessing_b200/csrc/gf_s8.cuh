@@ -84,6 +84,50 @@ __device__ __forceinline__ void gf_st8(float* p, const float2 (&v)[4])
                  : "memory");
 }
 #endif
+// ---- uint8 I/O (convertTo(CV_32F, 1/255) on load, convertTo(CV_8U, 255) on store,
+// main.cpp:121-122,158 fused into the kernel: 3 B/px instead of 12) ----------------------------------
+// The uint8 build works in the INTEGER domain: I' = 255 I, p' = 255 p are loaded as the floats 0..255.
+// a is scale-free, b' = 255 b, q' = mean_a I' + mean_b' = 255 q is exactly the value convertTo(CV_8U, 255)
+// rounds, and eps becomes 255^2 eps -- so neither conversion costs an operation.  Better than free: the
+// vertical running sums of I', p', I'p', I'I' are integers below 2^24, i.e. EXACT in float32 (no drift,
+// no re-seed), and so are the lane prefixes of the window sums; only sums above 2^24 (17 x 17 x 255^2
+// = 1.9e7) round, by at most one part in 2^24.
+__device__ __forceinline__ float gf_u8_to_f(unsigned word, int k)   // byte k of word as a float, no I2F:
+{                                                                   // 0x4B0000bb is the float 8388608 + bb
+#ifdef GF_CPU_EMU
+    return (float)((word >> (8 * k)) & 255u);
+#else
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 + k)) - 8388608.0f;
+#endif
+}
+__device__ __forceinline__ unsigned gf_f_to_u8(float q255)
+{
+#ifdef GF_CPU_EMU
+    const int r = (int)std::nearbyint(q255);
+#else
+    const int r = __float2int_rn(q255);                // cvRound: round half to even
+#endif
+    return (unsigned)(r < 0 ? 0 : (r > 255 ? 255 : r));   // saturate_cast<uchar>
+}
+__device__ __forceinline__ float gf_ld1(const float* p) { return *p; }
+__device__ __forceinline__ float gf_ld1(const unsigned char* p) { return (float)*p; }
+__device__ __forceinline__ void gf_st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void gf_st1(unsigned char* p, float v) { *p = (unsigned char)gf_f_to_u8(v); }
+__device__ __forceinline__ void gf_ld8(const unsigned char* p, float2 (&v)[4])
+{
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = make_float2(gf_u8_to_f(t.x, 0), gf_u8_to_f(t.x, 1));
+    v[1] = make_float2(gf_u8_to_f(t.x, 2), gf_u8_to_f(t.x, 3));
+    v[2] = make_float2(gf_u8_to_f(t.y, 0), gf_u8_to_f(t.y, 1));
+    v[3] = make_float2(gf_u8_to_f(t.y, 2), gf_u8_to_f(t.y, 3));
+}
+__device__ __forceinline__ void gf_st8(unsigned char* p, const float2 (&v)[4])
+{
+    uint2 t;
+    t.x = gf_f_to_u8(v[0].x) | (gf_f_to_u8(v[0].y) << 8) | (gf_f_to_u8(v[1].x) << 16) | (gf_f_to_u8(v[1].y) << 24);
+    t.y = gf_f_to_u8(v[2].x) | (gf_f_to_u8(v[2].y) << 8) | (gf_f_to_u8(v[3].x) << 16) | (gf_f_to_u8(v[3].y) << 24);
+    *reinterpret_cast<uint2*>(p) = t;
+}
 __device__ __forceinline__ float2 gf_neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 gf_dup2(float a) { return make_float2(a, a); }
 
@@ -179,9 +223,9 @@ struct GfS8Geom {
     static constexpr size_t ring_bytes = (size_t)KW * SLOT_F2 * 8;
 };
 
-template <int R>
+template <int R, class T = float>
 struct GfS8Ctx {
-    const float* gI; const float* gP; float* gQ;     // frame bases at (row buf_y0 / out_y0, this lane's first column)
+    const T* gI; const T* gP; T* gQ;     // frame bases at (row buf_y0 / out_y0, this lane's first column)
     int gs, ss, ds;                                  // row strides; (rows * stride) fits 31 bits (host check)
     float2* ring;                                    // this lane's cell of ring row 0
     int lane, x0, width, height, border, buf_y0, buf_ylast, out_y0, yi0;
@@ -225,13 +269,13 @@ __device__ __forceinline__ float gf_s8_rcp(float d)
 // 2 generic per-column border map (any border, any width; slow, rarely needed); 4 TRUNCATE border
 // (the class API): pixels outside the image contribute nothing and every mean divides by the number of
 // in-image pixels of its window (guided_filter_d.cu:251-262) -- zero-filled loads, per-pixel counts.
-template <int MODE, int R>
-__device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R>& c, const float* rowp, float2 (&v)[4])
+template <int MODE, int R, class T>
+__device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R, T>& c, const T* rowp, float2 (&v)[4])
 {
     if (MODE == 3) {
         float2 t[4];
         gf_ld8(rowp + c.vofs, t);
-        const float sc = rowp[c.sofs];
+        const float sc = gf_ld1(rowp + c.sofs);
         const float e[8] = {t[0].x, t[0].y, t[1].x, t[1].y, t[2].x, t[2].y, t[3].x, t[3].y};
         float d[8];
         // left of the image:  column -8k+j <- column 8k-j   = {sc, e7, e6, .., e1}
@@ -255,14 +299,14 @@ __device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R>& c, const float* rowp,
         gf_ld8(rowp, v);
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = make_float2(rowp[c.sx[2 * i]], rowp[c.sx[2 * i + 1]]);
+        for (int i = 0; i < 4; ++i) v[i] = make_float2(gf_ld1(rowp + c.sx[2 * i]), gf_ld1(rowp + c.sx[2 * i + 1]));
     }
 }
 
 // Row y (any integer) of both planes: REFLECT borders map the row index; MODE 4 (TRUNCATE) rows outside
 // the image are zeros.
-template <int MODE, int R>
-__device__ __forceinline__ void gf_s8_ld_row(const GfS8Ctx<R>& c, int y, float2 (&vI)[4], float2 (&vP)[4])
+template <int MODE, int R, class T>
+__device__ __forceinline__ void gf_s8_ld_row(const GfS8Ctx<R, T>& c, int y, float2 (&vI)[4], float2 (&vP)[4])
 {
     if (MODE == 4) {
         if (y < 0 || y > c.buf_ylast) {
@@ -291,18 +335,18 @@ __device__ __forceinline__ float gf_s8_cnt_y(int y, int height)
 }
 
 // c = f, f = 0: f holds exactly the rows of the current window, summed without a subtraction
-template <int R>
-__device__ __forceinline__ void gf_s8_reseed1(GfS8Ctx<R>& c)
+template <int R, class T>
+__device__ __forceinline__ void gf_s8_reseed1(GfS8Ctx<R, T>& c)
 {
-    if (!GF_S8_RESEED1) return;
+    if (!GF_S8_RESEED1 || sizeof(T) != 4) return;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         c.cI[i] = c.fI[i]; c.cP[i] = c.fP[i]; c.cIP[i] = c.fIP[i]; c.cII[i] = c.fII[i];
         c.fI[i] = c.fP[i] = c.fIP[i] = c.fII[i] = make_float2(0.f, 0.f);
     }
 }
-template <int R>
-__device__ __forceinline__ void gf_s8_reseed2(GfS8Ctx<R>& c)
+template <int R, class T>
+__device__ __forceinline__ void gf_s8_reseed2(GfS8Ctx<R, T>& c)
 {
     if (!GF_S8_RESEED2) return;
 #pragma unroll
@@ -317,8 +361,8 @@ __device__ __forceinline__ void gf_s8_reseed2(GfS8Ctx<R>& c)
 // stage 1 of input row yi = yi0 + t.  ONE copy of this code per strip mode serves the whole band
 // (instruction-cache footprint): ramp-up is data, not code -- the first a, b row (t = 2R) and the
 // first "old" row are zeros, and while `full` is false the ring is written but not subtracted.
-template <int R, int MODE>
-__device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool full)
+template <int R, int MODE, class T>
+__device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R, T>& c, int t, int slot, bool full)
 {
     using G = GfS8Geom<R>;
     constexpr int KW = G::KW, VL = G::VL;
@@ -338,7 +382,7 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
         c.cP[i] = gf_add2(c.cP[i], gf_sub2(c.nP[i], c.oP[i]));
         c.cIP[i] = gf_fma2(gf_neg2(c.oI[i]), c.oP[i], gf_fma2(c.nI[i], c.nP[i], c.cIP[i]));
         c.cII[i] = gf_fma2(gf_neg2(c.oI[i]), c.oI[i], gf_fma2(c.nI[i], c.nI[i], c.cII[i]));
-        if (GF_S8_RESEED1) {
+        if (GF_S8_RESEED1 && sizeof(T) == 4) {       // (uint8 build: integer sums below 2^24 are exact)
             c.fI[i] = gf_add2(c.fI[i], c.nI[i]);
             c.fP[i] = gf_add2(c.fP[i], c.nP[i]);
             c.fIP[i] = gf_fma2(c.nI[i], c.nP[i], c.fIP[i]);
@@ -355,8 +399,11 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
             const int rp = yi + 1 + GF_S8_PF;
             if (rp <= c.buf_ylast) {
                 const int op = rp - c.buf_y0;
-                gf_prefetch_l2(c.gI + op * c.gs + 24 * lane);
-                gf_prefetch_l2(c.gP + op * c.ss + 24 * lane);
+                constexpr int LINE = 128 / (int)sizeof(T);      // elements per 128-byte line
+                if (lane * LINE < 256) {
+                    gf_prefetch_l2(c.gI + op * c.gs + (LINE - 8) * lane);
+                    gf_prefetch_l2(c.gP + op * c.ss + (LINE - 8) * lane);
+                }
             }
         }
     }
@@ -404,15 +451,15 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
                     q[i] = gf_fma2(v, nh, gf_mul2(v, nl));
                 }
             }
-            float* pq = c.gQ + (yo - c.out_y0) * c.ds;
+            T* pq = c.gQ + (yo - c.out_y0) * c.ds;
             if (c.out_lane && !(GF_S8_ABL & 8)) {
                 if (!XMAP || c.vec_ok) {
                     gf_st8(pq, q);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        if (c.x0 + 2 * i >= 0 && c.x0 + 2 * i < c.width) pq[2 * i] = q[i].x;
-                        if (c.x0 + 2 * i + 1 >= 0 && c.x0 + 2 * i + 1 < c.width) pq[2 * i + 1] = q[i].y;
+                        if (c.x0 + 2 * i >= 0 && c.x0 + 2 * i < c.width) gf_st1(pq + 2 * i, q[i].x);
+                        if (c.x0 + 2 * i + 1 >= 0 && c.x0 + 2 * i + 1 < c.width) gf_st1(pq + 2 * i + 1, q[i].y);
                     }
                 }
             }
@@ -472,8 +519,8 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R>& c, int t, int slot, bool 
 // Warm-up rows t in [0, 2R): vertical accumulation only.  Nothing else is going on, so a single
 // row in flight would expose the full DRAM latency 2R times; rows are loaded CH at a time instead.
 // On entry nI/nP hold row yi0 (t = 0); on exit they hold row yi0 + 2R.
-template <int R, int MODE>
-__device__ __forceinline__ void gf_s8_warmup(GfS8Ctx<R>& c)
+template <int R, int MODE, class T>
+__device__ __forceinline__ void gf_s8_warmup(GfS8Ctx<R, T>& c)
 {
     constexpr int CH = 4, NROWS = 2 * R;
     float2 bI[CH][4], bP[CH][4];
@@ -503,8 +550,8 @@ __device__ __forceinline__ void gf_s8_warmup(GfS8Ctx<R>& c)
 // The row loop of one band: 2R warm-up rows, then iterations t = 2R .. steps in periods of 2R+1
 // (= ring length = re-seed period; the inner loop is straight-line code, `slot` is its counter).
 // The last iteration only needs its phase A; its phase B works on clamped rows and is discarded.
-template <int R, int MODE>
-__device__ __forceinline__ void gf_s8_band(GfS8Ctx<R>& c, int steps)
+template <int R, int MODE, class T>
+__device__ __forceinline__ void gf_s8_band(GfS8Ctx<R, T>& c, int steps)
 {
     constexpr int KW = 2 * R + 1;
     gf_s8_warmup<R, MODE>(c);
@@ -516,8 +563,8 @@ __device__ __forceinline__ void gf_s8_band(GfS8Ctx<R>& c, int steps)
 #pragma unroll 1
         for (int s = 0; s < n; ++s, ++t) gf_s8_iter<R, MODE>(c, t, s, full);
         if (n == KW) {
-            gf_s8_reseed1<R>(c);
-            gf_s8_reseed2<R>(c);
+            gf_s8_reseed1(c);
+            gf_s8_reseed2(c);
         }
         full = true;
     }
@@ -528,7 +575,7 @@ __device__ __forceinline__ void gf_s8_band(GfS8Ctx<R>& c, int steps)
 // analytic mirror (MODE 1) and all their lanes on that side produce output.  Otherwise strips
 // that overhang the image use mirror loads (MODE 3: REFLECT101, width % 8 == 0) or the generic
 // per-column border map (MODE 2).
-template <int R, int MINB>
+template <int R, int MINB, class T>
 __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
 {
     using G = GfS8Geom<R>;
@@ -541,7 +588,7 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
     const bool edge_ok = R == 8 && a.border == GF_REFLECT101 && (a.width & 7) == 0 && a.width >= G::WIN;
     const bool first = strip == 0, last = strip == a.nstrips - 1;
 
-    GfS8Ctx<R> c;
+    GfS8Ctx<R, T> c;
     c.lane = threadIdx.x & 31;
     int xl = strip * G::WOUT - 2 * H1 * 8, lane_lo = 2 * H1, col_min = 0;
     int mode = 0;
@@ -560,7 +607,9 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
     c.x0 = xl + 8 * c.lane;
     c.edge.left = mode == 1 && first && c.lane == 0;
     c.edge.right = mode == 1 && last && c.x0 + 8 == a.width;
-    c.gI = a.guide + f * a.gfs + c.x0; c.gP = a.src + f * a.sfs + c.x0; c.gQ = a.dst + f * a.dfs + c.x0;
+    // (GfWpArgs carries the planes as float*; T = unsigned char builds reinterpret them, strides are in elements)
+    c.gI = reinterpret_cast<const T*>(a.guide) + f * a.gfs + c.x0; c.gP = reinterpret_cast<const T*>(a.src) + f * a.sfs + c.x0;
+    c.gQ = reinterpret_cast<T*>(a.dst) + f * a.dfs + c.x0;
     c.gs = (int)a.gs; c.ss = (int)a.ss; c.ds = (int)a.ds;
     c.ring_lane = c.lane >= lane_lo && c.lane < lane_lo + VL;
     c.out_lane = c.ring_lane && c.x0 < a.width && c.x0 >= col_min;
@@ -582,7 +631,7 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
     const int yo0 = a.out_y0 + band * a.hb;
     const int yo1 = min(a.out_y0 + a.out_rows, yo0 + a.hb);
     c.yi0 = yo0 - 2 * R;
-    c.eps = a.eps;
+    c.eps = sizeof(T) == 4 ? a.eps : a.eps * 65025.0f;      // uint8 build: integer domain, eps scales with 255^2
     c.nk = gf_norm_make((float)(KW * KW));
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -635,7 +684,7 @@ static inline int gf_pick_band_rows(int rows, int r, long nstrips_x_count, long 
     return best_hb;
 }
 
-template <int R>
+template <int R, class T = float>
 static const char* gf_s8_launch(const Job& j)
 {
     using G = GfS8Geom<R>;
@@ -671,22 +720,25 @@ static const char* gf_s8_launch(const Job& j)
     dim3 grid((unsigned)items), block(32);
     constexpr int FIT = (int)((size_t)228 * 1024 / (G::ring_bytes + 1024));
     constexpr int MINB = FIT > 7 ? 7 : (FIT < 1 ? 1 : FIT);
-    auto k = gf_s8_gray_kernel<R, MINB>;
+    auto k = gf_s8_gray_kernel<R, MINB, T>;
     if (const char* e = gf_rt_set_smem(k, smem)) return e;
     GF_LAUNCH(k, grid, block, smem, j.stream, a);
     return gf_rt_launch_error();
 }
 
-static const char* gf_s8_try(const Job& j, bool* done, const char** name)
+// u8 = true: the planes hold unsigned char (Plane::ptr reinterpreted, strides in elements): uint8 in,
+// uint8 out, conversions fused into the loads and stores (gf_guided_gray_u8).
+static const char* gf_s8_try(const Job& j, bool* done, const char** name, bool u8 = false)
 {
     *done = false;
     if (j.color || j.A.ptr) return nullptr;
     if (j.border == GF_TRUNCATE && ((j.width & 7) || j.width < 256)) return nullptr;
-    if (getenv("GF_DISABLE_S8") || getenv("GF_DISABLE_FAST")) return nullptr;
+    if (!u8 && (getenv("GF_DISABLE_S8") || getenv("GF_DISABLE_FAST"))) return nullptr;
     const Plane* pl[3] = {&j.guide, &j.src, &j.dst};
+    const uintptr_t amask = u8 ? 7 : 31;                  // one 8-byte / 32-byte vector per lane and row
     for (int i = 0; i < 3; ++i)
         if (pl[i]->channels != 1 || pl[i]->coff != 0 || (pl[i]->stride & 7) || (pl[i]->frame_stride & 7) ||
-            ((uintptr_t)pl[i]->ptr & 31))
+            ((uintptr_t)pl[i]->ptr & amask))
             return nullptr;
     // row offsets inside a frame are 32-bit in the kernel
     if ((int64_t)j.buf_rows * j.guide.stride >= (1ll << 31) || (int64_t)j.buf_rows * j.src.stride >= (1ll << 31) ||
@@ -694,6 +746,14 @@ static const char* gf_s8_try(const Job& j, bool* done, const char** name)
         return nullptr;
     // single reflections only, and at least one full warp window of columns
     if (j.height < 4 * j.r + 2 || j.width < 4 * j.r + 2 || j.width < 64) return nullptr;
+    if (u8) {
+        switch (j.r) {
+#define GF_S8_CASE(RR) case RR: *done = true; *name = "s8u8_r" #RR; return gf_s8_launch<RR, unsigned char>(j);
+        GF_S8_CASE(4) GF_S8_CASE(7) GF_S8_CASE(8) GF_S8_CASE(16)
+#undef GF_S8_CASE
+        default: return nullptr;
+        }
+    }
     switch (j.r) {
 #define GF_S8_CASE(RR) case RR: *done = true; *name = "s8_r" #RR; return gf_s8_launch<RR>(j);
 #ifdef GF_CPU_EMU   // the test-only emulator build keeps its compile time down: one radius per code shape

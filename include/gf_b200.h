@@ -144,6 +144,16 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
 int gf_host_alloc(void** ptr, size_t bytes);
 int gf_host_free(void* ptr);
 
+/* ---- uint8 in / uint8 out ------------------------------------------------
+   The conversions the reference's demo does around the filter -- Mat::convertTo(CV_32F, 1/255) before
+   (main.cpp:121-122,205-206) and convertTo(CV_8U, 255) with saturating round-half-even after
+   (main.cpp:158,295-297) -- fused into the kernel's loads and stores: 3 bytes of HBM traffic per pixel
+   instead of 12.  Strides in ELEMENTS (= bytes).  Served by the s8 kernel only: r in {4,7,8,16},
+   width >= 64, height >= 4r+2, rows 8-byte aligned; other arguments return GF_ERR_UNSUPPORTED. */
+int gf_guided_gray_u8(const unsigned char* guide, const unsigned char* src, unsigned char* dst, int width, int height,
+                      int64_t guide_stride, int64_t src_stride, int64_t dst_stride, int r, float eps, int border,
+                      void* stream);
+
 /* ---- Integral/ module: summed-area table of a uint8 image ----------------
    Replace hIntegral / hAligned4Integral (Integral/integral_d.h:5-8, integral_d.cu:863-930):
    integral[y*dst_stride + x] = sum of src over rows <= y and columns <= x (inclusive, W x H).

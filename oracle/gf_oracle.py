@@ -240,3 +240,15 @@ def integral_u8(img, dtype=np.int64):
     if np.dtype(dtype) == np.int32:
         return (sat & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
     return sat.astype(dtype)
+
+
+# ---- uint8 in / uint8 out -----------------------------------------------------
+def u8_to_f32(img_u8):
+    """Mat::convertTo(CV_32F, 1.0/255.0) (main.cpp:121-122,205-206): float(x * (1.0/255.0)), the product in double."""
+    return (np.asarray(img_u8).astype(np.float64) * (1.0 / 255.0)).astype(np.float32)
+
+
+def guided_filter_gray_u8(I_u8, p_u8, r, eps, border=BORDER_REFLECT101):
+    """The reference demo's whole pipeline on 8-bit planes: convertTo float, the float32 CPU composition
+    (main.cpp:236-252), convertTo(CV_8U, 255) (main.cpp:295-297)."""
+    return to_u8(guided_filter_gray(u8_to_f32(I_u8), u8_to_f32(p_u8), r, eps, border, np.float32))
