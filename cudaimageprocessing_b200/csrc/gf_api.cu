@@ -236,6 +236,61 @@ struct gf_filter {
 };
 
 
+#ifdef GF_HAVE_FAST
+// The class API's multi-channel modes ((1,3): one gray guide for three source channels -- the reference's
+// own demo, main.cpp:141-150 -- and (3,3): channel by channel) on the tuned planar kernel: de-interleave the
+// source (and a 3-channel guide) into stream-ordered scratch planes, ONE s8 launch over the channels as
+// "frames" (a gray guide is shared: frame stride 0), re-interleave.  Returns false when the tuned kernel does
+// not take the job (the caller then runs the generic per-channel path); *rc is the status otherwise.
+static bool run_planar(const gf_filter& h, const float* guide, const float* src, float* dst, int64_t gs, int64_t ss, int64_t ds,
+                       int r, float eps, int border, void* stream, int* rc)
+{
+    const int w = h.width, hh = h.height, C = h.sch;
+    if (!(h.gch == 1 || h.gch == C) || C < 2 || C > 4) return false;
+    if (!guide || !src || !dst || r < 0 || !(eps >= 0.f)) return false;       // let the generic path report it
+    const int64_t pitch = ((int64_t)w + 7) / 8 * 8, plane = pitch * hh;
+    const int nplanes = 2 * C + (h.gch > 1 ? C : 0);
+    void* scratch = nullptr;
+    if (gf_rt_alloc_async(&scratch, (size_t)nplanes * plane * sizeof(float), stream)) return false;
+    float* sp = (float*)scratch;                 // [src planes | dst planes | guide planes]
+    float* dp = sp + (int64_t)C * plane;
+    float* gp = dp + (int64_t)C * plane;
+    Job j;
+    j.count = C;
+    j.width = w; j.height = hh; j.buf_rows = hh; j.out_rows = hh;
+    j.r = r; j.eps = eps; j.border = border; j.stream = stream;
+    j.guide = h.gch == 1 ? Plane{guide, gs, 0, 1, 0} : Plane{gp, pitch, plane, 1, 0};
+    j.src = Plane{sp, pitch, plane, 1, 0};
+    j.dst = Plane{dp, pitch, plane, 1, 0};
+    j.A = j.B = Plane{nullptr, 0, 0, 1, 0};
+    auto shuffle = [&](bool to_planar, const float* inter, int64_t stride, float* planar, int ch) {
+        GfIlArgs a;
+        a.inter = const_cast<float*>(inter); a.planar = planar; a.stride = stride; a.pitch = pitch; a.plane = plane;
+        a.width = w; a.height = hh; a.channels = ch;
+        dim3 block(256), grid(div_up(w, 256), hh < 2048 ? hh : 2048);
+        if (to_planar) { auto k = gf_interleave_kernel<true>; GF_LAUNCH(k, grid, block, 0, stream, a); }
+        else { auto k = gf_interleave_kernel<false>; GF_LAUNCH(k, grid, block, 0, stream, a); }
+    };
+    shuffle(true, src, ss, sp, C);
+    if (h.gch > 1) shuffle(true, guide, gs, gp, C);
+    bool done = false;
+    const char* name = nullptr;
+    const char* e = check_common(j) == GF_OK ? gf_s8_try(j, &done, &name) : nullptr;
+    if (!done) {                                   // not a job for the tuned kernel: nothing was written to dst
+        gf_rt_free_async(scratch, stream);
+        return false;
+    }
+    if (!e) shuffle(false, dst, ds, dp, C);
+    if (!e) e = gf_rt_launch_error();
+    gf_rt_free_async(scratch, stream);
+    if (e) { *rc = fail(GF_ERR_CUDA, "%s (planar class path): %s", name, e); return true; }
+    g_launches += 3 + (h.gch > 1 ? 1 : 0);
+    g_kernel = name;
+    *rc = GF_OK;
+    return true;
+}
+#endif
+
 template <class T>
 static int integral_entry(const unsigned char* src, T* integral, T* scratch, int sw, int sh, int w, int h, int64_t ss, int64_t ds,
                           void* stream, const char* name)
@@ -323,6 +378,12 @@ int gf_run(gf_handle h, const float* guide, const float* src, float* dst, int r,
     }
     // (1,1); (3,3) channel by channel; (1,3) one guide for three source channels
     // (guided_filter_d.cu:968-975)
+#ifdef GF_HAVE_FAST
+    if (h->sch > 1) {
+        int rc = GF_OK;
+        if (run_planar(*h, guide, src, dst, gs, ss, ds, r, eps, border, stream, &rc)) return rc;
+    }
+#endif
     Job js[3];
     for (int c = 0; c < h->sch; ++c) {
         js[c] = j;

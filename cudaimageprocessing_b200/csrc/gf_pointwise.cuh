@@ -45,3 +45,28 @@ __global__ void __launch_bounds__(256) gf_pointwise_kernel(const GfPwArgs a)
         }
     }
 }
+
+// ---- channel-interleaved <-> planar (the class API's (1,3)/(3,3) modes run the planar s8 kernel) ----
+// TO_PLANAR: planar[c][y][x] = inter[y*stride + x*C + c];  otherwise the reverse.  Thread per pixel,
+// 2-D grid-stride over rows; both sides are coalesced across the warp.
+struct GfIlArgs {
+    float* inter; float* planar;
+    int64_t stride;          // row stride of the interleaved buffer (floats)
+    int64_t pitch, plane;    // row pitch and plane size of the planar buffer (floats)
+    int width, height, channels;
+};
+
+template <bool TO_PLANAR>
+__global__ void __launch_bounds__(256) gf_interleave_kernel(const GfIlArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.width) return;
+    for (int y = blockIdx.y; y < a.height; y += gridDim.y) {
+        for (int c = 0; c < a.channels; ++c) {
+            float* pi = a.inter + (int64_t)y * a.stride + (int64_t)x * a.channels + c;
+            float* pp = a.planar + (int64_t)c * a.plane + (int64_t)y * a.pitch + x;
+            if (TO_PLANAR) *pp = *pi;
+            else *pi = *pp;
+        }
+    }
+}

@@ -12,7 +12,11 @@
 #define GF_LAUNCH(kernel, grid, block, smem, stream, ...) GF_EMU_LAUNCH(kernel, grid, block, smem, __VA_ARGS__)
 static inline const char* gf_rt_launch_error() { return nullptr; }
 template <class K> static inline const char* gf_rt_set_smem(K, size_t) { return nullptr; }
-static inline const char* gf_rt_alloc_async(void** p, size_t n, void*) { *p = std::malloc(n); return *p ? nullptr : "malloc failed"; }
+static inline const char* gf_rt_alloc_async(void** p, size_t n, void*)
+{   // 256-byte aligned like cudaMallocAsync (the tuned kernels check the alignment of every plane)
+    *p = std::aligned_alloc(256, (n + 255) / 256 * 256);
+    return *p ? nullptr : "malloc failed";
+}
 static inline void gf_rt_free_async(void* p, void*) { std::free(p); }
 static inline const char* gf_rt_copy2d_async(void* d, size_t dp, const void* s, size_t sp, size_t wb, size_t rows, void*)
 {

@@ -231,6 +231,21 @@ def test_class_run_channel_pairs(be):
     assert np.abs(q - O.guided_filter_color(g3, g1, 5, 0.05, O.BORDER_TRUNCATE)).max() <= TOL
 
 
+def test_class_run_planar_1080p(be):
+    """The reference's own path-A demo shape (main.cpp:109-150): 1080p, gray guide, 3-channel source,
+    r=7, eps=0.3 -- and the (3,3) mode -- take the planar s8 path."""
+    rng = np.random.default_rng(21)
+    g1 = rng.random((1080, 1920), dtype=np.float32)
+    g3 = rng.random((1080, 1920, 3), dtype=np.float32)
+    s3 = rng.random((1080, 1920, 3), dtype=np.float32)
+    for I in (g1, g3):
+        q = be.class_run(I, s3, 7, 0.3)
+        assert be.api.last_kernel() == "s8_r7"
+        ref = np.stack([C.guided_gray_f64(I if I.ndim == 2 else np.ascontiguousarray(I[:, :, c]), np.ascontiguousarray(s3[:, :, c]),
+                                          7, 0.3, 1, NT) for c in range(3)], axis=2)
+        assert np.abs(q - ref).max() <= TOL
+
+
 def test_batch_matches_single(be):
     rng = np.random.default_rng(8)
     I = rng.random((5, 270, 480, 3), dtype=np.float32)

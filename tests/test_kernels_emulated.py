@@ -260,3 +260,16 @@ def test_color_c4_batch(be):
     assert be.api.last_kernel() == "c4_r8"
     for k in range(2):
         assert np.abs(q[k] - O.guided_filter_color(I[k], p[k], 8, 1e-2, 0)).max() <= TOL
+
+
+def test_class_run_planar_path(be):
+    """The class API's (1,3) and (3,3) modes on the tuned kernel: channels de-interleaved into scratch
+    planes, one s8 launch over the channels, re-interleaved (TRUNCATE border, as GuidedFilter::run)."""
+    rng = np.random.default_rng(16)
+    g1 = rng.random((40, 264), dtype=np.float32)
+    g3 = rng.random((40, 264, 3), dtype=np.float32)
+    s3 = rng.random((40, 264, 3), dtype=np.float32)
+    for I in (g1, g3):
+        q = be.class_run(I, s3, 4, 0.05)
+        assert be.api.last_kernel() == "s8_r4"
+        assert np.abs(q - O.guided_filter_class_run(I, s3, 4, 0.05)).max() <= TOL
