@@ -87,14 +87,6 @@ def main():
             ms = e0.elapsed_time(e1) / 3
             out.append({"case": "color_batch", "frames": n, "r": r, "kernel": api.last_kernel(), "ms": ms, "gpix_s": n * 1920 * 1080 / ms / 1e6, "gbs_alg": 20.0 * n * 1920 * 1080 / ms / 1e6})
             print(json.dumps(out[-1]), flush=True)
-    if "k8" in cases:
-        for wps in (4, 5, 6, 7, 8, 12, 14):
-            out.append(time_gray(3840, 2160, 8, env={"GF_WP_K8": 1, "GF_WP_WARPS_PER_SM": wps}))
-            print(json.dumps(out[-1]), flush=True)
-        for env in ({"GF_WP_K8": 1}, {}):
-            for (w, h, r) in [(7680, 4320, 8), (3840, 2160, 16), (7680, 4320, 16), (1920, 1080, 8)]:
-                out.append(time_gray(w, h, r, nsets=3 if w * h > 3e7 else 6, iters=20, env=env))
-                print(json.dumps(out[-1]), flush=True)
     if cases and cases[0] == "custom":      # custom W H R [iters]  (kernel env vars come from the shell)
         w, h, r = int(cases[1]), int(cases[2]), int(cases[3])
         it = int(cases[4]) if len(cases) > 4 else 6

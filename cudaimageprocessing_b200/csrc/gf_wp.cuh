@@ -9,11 +9,10 @@
 // L1/L2 hits and cheap FADDs; what they buy back is the barrier stall that dominated the
 // exchange version (profiles/).
 //
-// K = 4: one float4 per lane and plane, 4 warps per CTA, 12-16 warps per SM.
-// K = 8: two float4 per lane and plane; halo shrinks to 1 lane per side and stage at r <= 8 (28
-//        of 32 lanes produce output instead of 24) and the window sums need 16 shuffles per 8
-//        columns instead of 2*10: ~1.7x fewer instructions per pixel, paid for with registers
-//        (1 warp per CTA, 7 warps per SM, each with twice the independent work).
+// K = 4 is what this file launches: one float4 per lane and plane, 4 warps per CTA, 12-16 warps per SM
+// (first-generation kernel; the fallback for A/B outputs, 16-byte-only alignment and TRUNCATE jobs
+// the s8 kernel does not take).  The K-generic window sums below also serve gf_s8.cuh (K = 8) for radii
+// that are not multiples of 8.
 //
 // The row loop is cut into phases with compile-time stage flags so that a warp whose band and
 // columns are interior runs straight-line code: no border mapping, no predicates on t, constant
@@ -460,7 +459,6 @@ static const char* gf_wp_try(const Job& j, bool* done, const char** name)
             return nullptr;
     if (j.A.ptr && (j.A.channels != 1 || j.A.coff != 0)) return nullptr;
     *done = true;
-    const bool k8 = getenv("GF_WP_K8") != nullptr;
     switch (j.r) {
     case 1: *name = "wp_r1"; return gf_wp_launch<1, 4>(j);
     case 2: *name = "wp_r2"; return gf_wp_launch<2, 4>(j);
@@ -469,9 +467,7 @@ static const char* gf_wp_try(const Job& j, bool* done, const char** name)
     case 5: *name = "wp_r5"; return gf_wp_launch<5, 4>(j);
     case 6: *name = "wp_r6"; return gf_wp_launch<6, 4>(j);
     case 7: *name = "wp_r7"; return gf_wp_launch<7, 4>(j);
-    case 8:
-        if (k8) { *name = "wp8_r8"; return gf_wp_launch<8, 8>(j); }
-        *name = "wp_r8"; return gf_wp_launch<8, 4>(j);
+    case 8: *name = "wp_r8"; return gf_wp_launch<8, 4>(j);
     case 9: *name = "wp_r9"; return gf_wp_launch<9, 4>(j);
     case 10: *name = "wp_r10"; return gf_wp_launch<10, 4>(j);
     case 11: *name = "wp_r11"; return gf_wp_launch<11, 4>(j);
@@ -479,9 +475,7 @@ static const char* gf_wp_try(const Job& j, bool* done, const char** name)
     case 13: *name = "wp_r13"; return gf_wp_launch<13, 4>(j);
     case 14: *name = "wp_r14"; return gf_wp_launch<14, 4>(j);
     case 15: *name = "wp_r15"; return gf_wp_launch<15, 4>(j);
-    default:
-        if (k8) { *name = "wp8_r16"; return gf_wp_launch<16, 8>(j); }
-        *name = "wp_r16"; return gf_wp_launch<16, 4>(j);
+    default: *name = "wp_r16"; return gf_wp_launch<16, 4>(j);
     }
 }
 #endif  // GF_NO_HOST

@@ -184,17 +184,6 @@ def test_gray_fast_steady_path(be, shape, r, border, monkeypatch):
     assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
 
 
-@pytest.mark.parametrize("shape,r,border", [((120, 700), 8, 0), ((40, 300), 8, 1), ((150, 600), 16, 2)])
-def test_gray_wp_k8(be, shape, r, border, monkeypatch):
-    """the 8-columns-per-lane build of the warp-private kernel (GF_WP_K8): interior and border warps."""
-    monkeypatch.setenv("GF_WP_K8", "1")
-    monkeypatch.setenv("GF_DISABLE_S8", "1")
-    I, p = synth_pair(*shape, seed=61, kind="structured")
-    q = be.guided_gray(I, p, r, 1e-2, border)
-    assert be.api.last_kernel() == f"wp8_r{r}"
-    assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
-
-
 # ---- the headline kernel (gf_s8.cuh: 8 columns per lane) under the emulator ----------------------
 @pytest.mark.parametrize("shape,r,border", [((60, 700), 8, 0), ((75, 512), 8, 2), ((64, 256), 8, 0), ((50, 480), 8, 0), ((45, 472), 8, 0), ((40, 224), 8, 0), ((90, 1000), 8, 0),
                                             ((50, 264), 7, 0), ((70, 520), 7, 2), ((30, 300), 4, 0), ((40, 320), 4, 0), ((100, 640), 16, 0), ((140, 512), 32, 0),
