@@ -130,6 +130,64 @@ def test_color_1080p_r16(be, border):
     assert err <= TOL
 
 
+def test_fuzz_s8_against_generic_kernel(be, monkeypatch):
+    """Differential fuzz: 150 random (shape, radius, border, row padding) jobs through the tuned kernels
+    and through the generic kernel (a different algorithm: thread per column, scan-based window sums).
+    Catches geometry corner cases (strip/band boundaries, which strip mode an edge strip takes...)."""
+    import torch
+    rng = np.random.default_rng(2024)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    worst = 0.0
+    for it in range(150):
+        r = int(rng.choice(S8_RADII))
+        h = int(rng.integers(4 * r + 2, 4 * r + 400))
+        w = int(rng.integers(64, 2300))
+        border = int(rng.integers(0, 3))
+        s_ = (w + 7) // 8 * 8 + 8 * int(rng.integers(0, 3))
+        I = torch.rand((h, s_), device="cuda", generator=g)
+        p = torch.rand((h, s_), device="cuda", generator=g)
+        q1, q0 = torch.empty_like(I), torch.empty_like(I)
+        be.api.call("gf_guided_gray", I.data_ptr(), p.data_ptr(), q1.data_ptr(), None, None, w, h, s_, s_, s_, 0, r, 1e-2, border, None)
+        k1 = be.api.last_kernel()
+        monkeypatch.setenv("GF_DISABLE_FAST", "1")
+        be.api.call("gf_guided_gray", I.data_ptr(), p.data_ptr(), q0.data_ptr(), None, None, w, h, s_, s_, s_, 0, r, 1e-2, border, None)
+        monkeypatch.delenv("GF_DISABLE_FAST")
+        torch.cuda.synchronize()
+        assert be.api.last_kernel().startswith("generic")
+        d = float((q1[:, :w] - q0[:, :w]).abs().max())
+        assert d <= 2e-5, (it, h, w, r, border, s_, k1, d)
+        worst = max(worst, d)
+    print(f"fuzz: worst |tuned - generic| = {worst:.2e}")
+
+
+def test_fuzz_c4_against_generic_kernel(be, monkeypatch):
+    """The same differential fuzz for the tuned colour-guide kernel (batches of 1-3 frames)."""
+    import torch
+    rng = np.random.default_rng(77)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    worst = 0.0
+    for it in range(40):
+        r = int(rng.choice([4, 8, 12, 16]))
+        h = int(rng.integers(4 * r + 2, 4 * r + 200))
+        w = 4 * int(rng.integers(32, 400))
+        n = int(rng.integers(1, 4))
+        I = torch.rand((n, h, w, 3), device="cuda", generator=g)
+        p = torch.rand((n, h, w), device="cuda", generator=g)
+        q1, q0 = torch.empty_like(p), torch.empty_like(p)
+        args = (n, w, h, 3, 0, 0, 0, 0, 0, 0, r, 1e-2, 0, None)
+        be.api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q1.data_ptr(), *args)
+        assert be.api.last_kernel() == f"c4_r{r}"
+        monkeypatch.setenv("GF_DISABLE_FAST", "1")
+        be.api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q0.data_ptr(), *args)
+        monkeypatch.delenv("GF_DISABLE_FAST")
+        torch.cuda.synchronize()
+        assert be.api.last_kernel() == "generic_color"
+        d = float((q1 - q0).abs().max())
+        assert d <= 5e-5, (it, n, h, w, r, d)
+        worst = max(worst, d)
+    print(f"fuzz colour: worst |tuned - generic| = {worst:.2e}")
+
+
 def test_no_out_of_bounds_access(be):
     """(compute-sanitizer is closed on this pool.)  Every plane sits inside a larger allocation whose
     guard rows and row padding are NaN: a read outside the image poisons q, a write outside the
