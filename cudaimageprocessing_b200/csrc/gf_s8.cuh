@@ -48,6 +48,12 @@
 #define GF_S8_SHFL_UP(v, d) __shfl_up_sync(0xffffffffu, v, d)
 #define GF_S8_SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, v, d)
 #endif
+#ifndef GF_S8_EDGE_PCT_ANALYTIC
+#define GF_S8_EDGE_PCT_ANALYTIC 78    // band height of the two edge strips, % of the interior strips' (r = 8, REFLECT101)
+#endif
+#ifndef GF_S8_EDGE_PCT_OTHER
+#define GF_S8_EDGE_PCT_OTHER 55       // ... for the other edge modes (mirror loads, clipped counts, column map)
+#endif
 #ifndef GF_S8_PF
 #define GF_S8_PF 4            // rows ahead for the L2 prefetch hint (0 = off)
 #endif
@@ -582,9 +588,23 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
     constexpr int H1 = G::H1, KW = G::KW, VL = G::VL;
     GF_DYN_SMEM(float, smem);
     const long item = (long)blockIdx.x;
-    const long per_frame = (long)a.nstrips * a.nbands;
+    // Work items of a frame: the first and the last strip (slower code: image edges) come first and in
+    // nbands_e bands of hb_e rows, the interior strips follow in nbands bands of hb rows -- so that all
+    // warps of the single wave finish together (the kernel is as slow as its slowest warp).
+    const bool two = a.nbands_e > 0 && a.nstrips >= 3;
+    const long n_edge = two ? 2L * a.nbands_e : 0, n_int = two ? (long)(a.nstrips - 2) * a.nbands : (long)a.nstrips * a.nbands;
+    const long per_frame = n_edge + n_int;
     const int64_t f = item / per_frame;
-    const int band = (int)((item % per_frame) / a.nstrips), strip = (int)(item % a.nstrips);
+    const long idx = item % per_frame;
+    int band, strip, hbw;
+    if (idx < n_edge) {
+        band = (int)(idx >> 1); strip = (idx & 1) ? a.nstrips - 1 : 0; hbw = a.hb_e;
+    } else if (two) {
+        const long k = idx - n_edge;
+        band = (int)(k / (a.nstrips - 2)); strip = 1 + (int)(k % (a.nstrips - 2)); hbw = a.hb;
+    } else {
+        band = (int)(idx / a.nstrips); strip = (int)(idx % a.nstrips); hbw = a.hb;
+    }
     const bool edge_ok = R == 8 && a.border == GF_REFLECT101 && (a.width & 7) == 0 && a.width >= G::WIN;
     const bool first = strip == 0, last = strip == a.nstrips - 1;
 
@@ -598,7 +618,7 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
         if (last && !first) { xl = a.width - G::WIN; lane_lo = 4 * H1; col_min = strip * G::WOUT; }
     } else if (a.border == GF_TRUNCATE) {
         // interior warps (every window they touch is full) run the plain code; the others count pixels
-        const int by0 = a.out_y0 + band * a.hb, by1 = min(a.out_y0 + a.out_rows, by0 + a.hb);
+        const int by0 = a.out_y0 + band * hbw, by1 = min(a.out_y0 + a.out_rows, by0 + hbw);
         const bool inside = xl >= 0 && xl + G::WIN <= a.width && by0 - 2 * R >= 0 && by1 + 2 * R <= a.height;
         mode = inside ? 0 : 4;
     } else if (xl < 0 || xl + G::WIN > a.width) {
@@ -628,8 +648,8 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
     c.out_r = mode == 3 && c.x0 >= a.width;
     c.vofs = c.out_l ? -2 * c.x0 - 8 : (c.out_r ? 2 * a.width - 8 - 2 * c.x0 : 0);
     c.sofs = c.out_l ? -2 * c.x0 : (c.out_r ? 2 * a.width - 9 - 2 * c.x0 : 0);
-    const int yo0 = a.out_y0 + band * a.hb;
-    const int yo1 = min(a.out_y0 + a.out_rows, yo0 + a.hb);
+    const int yo0 = a.out_y0 + band * hbw;
+    const int yo1 = min(a.out_y0 + a.out_rows, yo0 + hbw);
     c.yi0 = yo0 - 2 * R;
     c.eps = sizeof(T) == 4 ? a.eps : a.eps * 65025.0f;      // uint8 build: integer domain, eps scales with 255^2
     c.nk = gf_norm_make((float)(KW * KW));
@@ -716,7 +736,30 @@ static const char* gf_s8_launch(const Job& j)
     if (hb > j.out_rows) hb = j.out_rows;
     a.hb = hb;
     a.nbands = (j.out_rows + hb - 1) / hb;
-    const long items = (long)a.nstrips * a.nbands * j.count;
+    // The two edge strips run slower code (analytic edges at r = 8: +30 % instructions; mirror loads /
+    // clipped counts otherwise, ~1.8x the time per row): they get shorter bands, in proportion.  Measured on B200
+    // (profiles/r1_s8_edge_band_pct.txt): 4K r=16 125 -> 90 us, 8K r=32 780 -> 493 us, 4K r=8 66.2 -> 65.1 us.
+    int edge_pct = (R == 8 && j.border == GF_REFLECT101) ? GF_S8_EDGE_PCT_ANALYTIC : GF_S8_EDGE_PCT_OTHER;
+    if (const char* e = getenv("GF_S8_EDGE_PCT")) edge_pct = atoi(e);
+    a.hb_e = 0; a.nbands_e = 0;
+    if (a.nstrips >= 3 && edge_pct > 0 && edge_pct < 100 && a.nbands > 1) {
+        const long slots = (long)sms * warps_sm;
+        const bool one_wave = (long)a.nstrips * a.nbands * j.count <= slots;
+        for (;;) {
+            int hbe = hb * edge_pct / 100;
+            if (hbe < hb_min) hbe = hb_min;
+            if (hbe >= hb) { a.hb_e = 0; a.nbands_e = 0; break; }
+            a.hb_e = hbe; a.nbands_e = (j.out_rows + hbe - 1) / hbe;
+            a.nbands = (j.out_rows + hb - 1) / hb;
+            const long items = (2L * a.nbands_e + (long)(a.nstrips - 2) * a.nbands) * j.count;
+            if (!one_wave || items <= slots || hb >= j.out_rows) break;     // a job that fitted one wave must still fit
+            ++hb;
+        }
+        a.hb = hb;
+        a.nbands = (j.out_rows + hb - 1) / hb;
+    }
+    const long per_frame = a.nbands_e > 0 ? 2L * a.nbands_e + (long)(a.nstrips - 2) * a.nbands : (long)a.nstrips * a.nbands;
+    const long items = per_frame * j.count;
     dim3 grid((unsigned)items), block(32);
     constexpr int FIT = (int)((size_t)228 * 1024 / (G::ring_bytes + 1024));
     constexpr int MINB = FIT > 7 ? 7 : (FIT < 1 ? 1 : FIT);

@@ -125,6 +125,7 @@ struct GfWpArgs {
     int64_t gfs, sfs, dfs, abfs;
     int width, height, buf_y0, buf_rows, out_y0, out_rows, border, hb;
     int nstrips, nbands, count;
+    int hb_e, nbands_e;      // gf_s8 only: band height / band count of the first and last strip (0 = same as the others)
     float eps;
 };
 

@@ -202,6 +202,17 @@ def test_gray_s8(be, shape, r, border, monkeypatch):
     assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
 
 
+@pytest.mark.parametrize("shape,r,border", [((90, 1000), 8, 0), ((100, 960), 4, 0), ((120, 1000), 8, 1)])
+def test_gray_s8_two_band_classes(be, shape, r, border, monkeypatch):
+    """the first and last strip in shorter bands than the interior strips (GF_S8_EDGE_PCT): item -> (strip, band) mapping"""
+    monkeypatch.setenv("GF_S8_HB", "40")
+    monkeypatch.setenv("GF_S8_EDGE_PCT", "65")
+    I, p = synth_pair(*shape, seed=73, kind="structured")
+    q = be.guided_gray(I, p, r, 1e-2, border)
+    assert be.api.last_kernel() == f"s8_r{r}"
+    assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
+
+
 def test_gray_s8_batch_strip_kat(be):
     rng = np.random.default_rng(8)
     Ib = rng.random((2, 40, 320), dtype=np.float32)
