@@ -129,8 +129,8 @@ __device__ __forceinline__ void gf_c4_load_row(const GfC4Ctx<R>& c, int y, float
     int rn = gf_s8_map_y(y, c.height, c.border);
     rn = rn > c.buf_ylast ? c.buf_ylast : rn;
     const int o = rn - c.buf_y0;
-    gf_c4_ld<R>(c, o * c.gs, o * c.ss, vi, vp);
-    if (MIRROR) gf_c4_mirror<R>(c, vi, vp);
+    gf_c4_ld<R>(c, o * c.gs, o * c.ss, vi, vp);     // RAW for lanes outside the image: gf_c4_mirror runs where the row is
+                                                    // consumed (shuffles right behind the loads would wait for them here)
 }
 
 // the 13 products of one pixel, added to (SUB = false) or removed from (SUB = true) the column sums
@@ -153,6 +153,7 @@ __device__ __forceinline__ void gf_c4_iter(GfC4Ctx<R>& c, int t, int slot, bool 
     constexpr int KW = G::KW, VL = G::VL;
     const int yi = c.yi0 + t;
 
+    if (MIRROR) { gf_c4_mirror<R>(c, c.nI, c.nP); gf_c4_mirror<R>(c, c.oI, c.oP); }
     // ---- stage 1, vertical: add row yi, drop row yi - KW (its guide pixels are kept for the output)
     float gI[12];
 #pragma unroll
@@ -239,6 +240,7 @@ __device__ __forceinline__ void gf_c4_band(GfC4Ctx<R>& c, int steps)
             for (int k = 0; k < 4; ++k) gf_c4_load_row<R, MIRROR>(c, c.yi0 + t + 1 + k, bI[k], bP[k]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+                if (MIRROR) gf_c4_mirror<R>(c, c.nI, c.nP);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) gf_c4_accum<false>(c.c, j, c.nI[3 * j], c.nI[3 * j + 1], c.nI[3 * j + 2], c.nP[j]);
 #pragma unroll

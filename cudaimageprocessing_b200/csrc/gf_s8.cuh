@@ -52,7 +52,7 @@
 #define GF_S8_EDGE_PCT_ANALYTIC 78    // band height of the two edge strips, % of the interior strips' (r = 8, REFLECT101)
 #endif
 #ifndef GF_S8_EDGE_PCT_OTHER
-#define GF_S8_EDGE_PCT_OTHER 55       // ... for the other edge modes (mirror loads, clipped counts, column map)
+#define GF_S8_EDGE_PCT_OTHER 85       // ... for the other edge modes (mirror loads, clipped counts, column map)
 #endif
 #ifndef GF_S8_PF
 #define GF_S8_PF 4            // rows ahead for the L2 prefetch hint (0 = off)
@@ -119,13 +119,37 @@ __device__ __forceinline__ float gf_ld1(const float* p) { return *p; }
 __device__ __forceinline__ float gf_ld1(const unsigned char* p) { return (float)*p; }
 __device__ __forceinline__ void gf_st1(float* p, float v) { *p = v; }
 __device__ __forceinline__ void gf_st1(unsigned char* p, float v) { *p = (unsigned char)gf_f_to_u8(v); }
+__device__ __forceinline__ float gf_bits_f(unsigned u)
+{
+#ifdef GF_CPU_EMU
+    float f; std::memcpy(&f, &u, 4); return f;
+#else
+    return __uint_as_float(u);
+#endif
+}
+__device__ __forceinline__ unsigned gf_f_bits(float f)
+{
+#ifdef GF_CPU_EMU
+    unsigned u; std::memcpy(&u, &f, 4); return u;
+#else
+    return __float_as_uint(f);
+#endif
+}
+// 8 pixels = 8 bytes, kept RAW in v[0] (two registers); gf_u8_expand converts them where the row is consumed,
+// one iteration later -- a conversion right behind the load would make the warp wait for the load there.
 __device__ __forceinline__ void gf_ld8(const unsigned char* p, float2 (&v)[4])
 {
     const uint2 t = *reinterpret_cast<const uint2*>(p);
-    v[0] = make_float2(gf_u8_to_f(t.x, 0), gf_u8_to_f(t.x, 1));
-    v[1] = make_float2(gf_u8_to_f(t.x, 2), gf_u8_to_f(t.x, 3));
-    v[2] = make_float2(gf_u8_to_f(t.y, 0), gf_u8_to_f(t.y, 1));
-    v[3] = make_float2(gf_u8_to_f(t.y, 2), gf_u8_to_f(t.y, 3));
+    v[0] = make_float2(gf_bits_f(t.x), gf_bits_f(t.y));
+    v[1] = v[2] = v[3] = make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ void gf_u8_expand(float2 (&v)[4])
+{
+    const unsigned x = gf_f_bits(v[0].x), y = gf_f_bits(v[0].y);
+    v[0] = make_float2(gf_u8_to_f(x, 0), gf_u8_to_f(x, 1));
+    v[1] = make_float2(gf_u8_to_f(x, 2), gf_u8_to_f(x, 3));
+    v[2] = make_float2(gf_u8_to_f(y, 0), gf_u8_to_f(y, 1));
+    v[3] = make_float2(gf_u8_to_f(y, 2), gf_u8_to_f(y, 3));
 }
 __device__ __forceinline__ void gf_st8(unsigned char* p, const float2 (&v)[4])
 {
@@ -247,6 +271,7 @@ struct GfS8Ctx {
     float2 cI[4], cP[4], cIP[4], cII[4], sA[4], sB[4], va[4], vb[4];
     float2 fI[4], fP[4], fIP[4], fII[4], fA[4], fB[4];   // re-seed accumulators
     float2 nI[4], nP[4], oI[4], oP[4];               // oI doubles as the guide row of the next output
+    float sc[4];                                     // MODE 3 only: the mirror scalar of nI, nP, oI, oP (rows are held raw)
 };
 
 // single reflection (callers guarantee |overshoot| < n)
@@ -276,24 +301,14 @@ __device__ __forceinline__ float gf_s8_rcp(float d)
 // (the class API): pixels outside the image contribute nothing and every mean divides by the number of
 // in-image pixels of its window (guided_filter_d.cu:251-262) -- zero-filled loads, per-pixel counts.
 template <int MODE, int R, class T>
-__device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R, T>& c, const T* rowp, float2 (&v)[4])
+__device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R, T>& c, const T* rowp, float2 (&v)[4], float& sc)
 {
     if (MODE == 3) {
-        float2 t[4];
-        gf_ld8(rowp + c.vofs, t);
-        const float sc = gf_ld1(rowp + c.sofs);
-        const float e[8] = {t[0].x, t[0].y, t[1].x, t[1].y, t[2].x, t[2].y, t[3].x, t[3].y};
-        float d[8];
-        // left of the image:  column -8k+j <- column 8k-j   = {sc, e7, e6, .., e1}
-        // right of the image: column W+8m+j <- W-2-8m-j     = {e6, e5, .., e0, sc}
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float lv = j == 0 ? sc : e[8 - j];
-            const float rv = j == 7 ? sc : e[6 - j];
-            d[j] = c.out_l ? lv : (c.out_r ? rv : e[j]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = make_float2(d[2 * i], d[2 * i + 1]);
+        // RAW mirror data: the permutation is applied where the row is consumed (gf_s8_fix), one iteration later --
+        // selects right behind the loads would make the warp wait for them here and expose the memory latency
+        gf_ld8(rowp + c.vofs, v);
+        sc = 0.f;                                       // only the lanes outside the image need the scalar (a predicated
+        if (c.out_l || c.out_r) sc = gf_ld1(rowp + c.sofs);   // load: 1-2 wavefronts instead of 8 for the whole warp)
     } else if (MODE == 4) {
         if (c.lane_in) {
             gf_ld8(rowp, v);
@@ -309,10 +324,41 @@ __device__ __forceinline__ void gf_s8_ld(const GfS8Ctx<R, T>& c, const T* rowp, 
     }
 }
 
+// MODE 3: raw mirror data -> the lane's 8 columns
+//   left of the image:  column -8k+j <- column 8k-j   = {sc, e7, e6, .., e1}
+//   right of the image: column W+8m+j <- W-2-8m-j     = {e6, e5, .., e0, sc}
+template <int MODE, int R, class T>
+__device__ __forceinline__ void gf_s8_fix(const GfS8Ctx<R, T>& c, float2 (&v)[4], float sc)
+{
+    if (sizeof(T) == 1) {                               // uint8 build: the vector part of the row is still raw bytes
+        if (MODE == 2) {                                // (lanes that gathered column by column already hold floats)
+            float2 t[4] = {v[0], v[1], v[2], v[3]};
+            gf_u8_expand(t);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = c.vec_ok ? t[i] : v[i];
+        } else if (MODE == 4) {
+            if (c.lane_in) gf_u8_expand(v);
+        } else {
+            gf_u8_expand(v);
+        }
+    }
+    if (MODE != 3) return;
+    const float e[8] = {v[0].x, v[0].y, v[1].x, v[1].y, v[2].x, v[2].y, v[3].x, v[3].y};
+    float d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float lv = j == 0 ? sc : e[8 - j];
+        const float rv = j == 7 ? sc : e[6 - j];
+        d[j] = c.out_l ? lv : (c.out_r ? rv : e[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = make_float2(d[2 * i], d[2 * i + 1]);
+}
+
 // Row y (any integer) of both planes: REFLECT borders map the row index; MODE 4 (TRUNCATE) rows outside
 // the image are zeros.
 template <int MODE, int R, class T>
-__device__ __forceinline__ void gf_s8_ld_row(const GfS8Ctx<R, T>& c, int y, float2 (&vI)[4], float2 (&vP)[4])
+__device__ __forceinline__ void gf_s8_ld_row(const GfS8Ctx<R, T>& c, int y, float2 (&vI)[4], float2 (&vP)[4], float& scI, float& scP)
 {
     if (MODE == 4) {
         if (y < 0 || y > c.buf_ylast) {
@@ -321,14 +367,14 @@ __device__ __forceinline__ void gf_s8_ld_row(const GfS8Ctx<R, T>& c, int y, floa
             return;
         }
         const int o = y - c.buf_y0;
-        gf_s8_ld<MODE>(c, c.gI + o * c.gs, vI);
-        gf_s8_ld<MODE>(c, c.gP + o * c.ss, vP);
+        gf_s8_ld<MODE>(c, c.gI + o * c.gs, vI, scI);
+        gf_s8_ld<MODE>(c, c.gP + o * c.ss, vP, scP);
     } else {
         int rn = gf_s8_map_y(y, c.height, c.border);
         rn = rn > c.buf_ylast ? c.buf_ylast : rn;
         const int o = rn - c.buf_y0;
-        gf_s8_ld<MODE>(c, c.gI + o * c.gs, vI);
-        gf_s8_ld<MODE>(c, c.gP + o * c.ss, vP);
+        gf_s8_ld<MODE>(c, c.gI + o * c.gs, vI, scI);
+        gf_s8_ld<MODE>(c, c.gP + o * c.ss, vP, scP);
     }
 }
 
@@ -379,6 +425,8 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R, T>& c, int t, int slot, bo
     // ================= phase B, part 1: vertical sums of row yi =================
     // (first, so that the loads of the next iteration can be issued right away and have a whole
     // iteration to land)
+    gf_s8_fix<MODE>(c, c.nI, c.sc[0]); gf_s8_fix<MODE>(c, c.nP, c.sc[1]);
+    gf_s8_fix<MODE>(c, c.oI, c.sc[2]); gf_s8_fix<MODE>(c, c.oP, c.sc[3]);
     float2 gI[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) gI[i] = c.oI[i];
@@ -397,8 +445,8 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R, T>& c, int t, int slot, bo
     }
     // rows of the next iteration, consumed at the top of it
     if (!(GF_S8_ABL & 4)) {
-        gf_s8_ld_row<MODE>(c, yi + 1, c.nI, c.nP);
-        gf_s8_ld_row<MODE>(c, yi + 1 - KW, c.oI, c.oP);
+        gf_s8_ld_row<MODE>(c, yi + 1, c.nI, c.nP, c.sc[0], c.sc[1]);
+        gf_s8_ld_row<MODE>(c, yi + 1 - KW, c.oI, c.oP, c.sc[2], c.sc[3]);
         if (GF_S8_PF > 0 && MODE <= 1 && lane < 8) {
             // L2 prefetch hint a few rows ahead: 8 lanes x one 128-byte line = the warp's 256 columns.
             // (Measured: +3% over no hint; a hint per 32-byte sector from all 32 lanes is 10% SLOWER.)
@@ -530,16 +578,19 @@ __device__ __forceinline__ void gf_s8_warmup(GfS8Ctx<R, T>& c)
 {
     constexpr int CH = 4, NROWS = 2 * R;
     float2 bI[CH][4], bP[CH][4];
+    float bsI[CH], bsP[CH];
 #pragma unroll 1
     for (int t0 = 0; t0 < NROWS; t0 += CH) {
         // rows t0+1 .. t0+CH  (row t0 is already in nI/nP)
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
-            gf_s8_ld_row<MODE>(c, c.yi0 + t0 + 1 + k, bI[k], bP[k]);
+            gf_s8_ld_row<MODE>(c, c.yi0 + t0 + 1 + k, bI[k], bP[k], bsI[k], bsP[k]);
         }
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
             if (t0 + k < NROWS) {
+                gf_s8_fix<MODE>(c, c.nI, c.sc[0]); gf_s8_fix<MODE>(c, c.nP, c.sc[1]);
+                c.sc[0] = bsI[k]; c.sc[1] = bsP[k];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     c.cI[i] = gf_add2(c.cI[i], c.nI[i]);
@@ -659,22 +710,23 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
         c.fI[i] = c.fP[i] = c.fIP[i] = c.fII[i] = c.fA[i] = c.fB[i] = make_float2(0.f, 0.f);
         c.oI[i] = c.oP[i] = make_float2(0.f, 0.f);
     }
+    c.sc[0] = c.sc[1] = c.sc[2] = c.sc[3] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) c.sx[j] = mode == 2 ? gf_map(c.x0 + j, a.width, a.border) - c.x0 : j;
 
     const int steps = (yo1 - yo0) + 4 * R;
     const int o0 = gf_s8_map_y(c.yi0, a.height, a.border) - a.buf_y0;       // row of iteration 0
     if (mode == 2) {
-        gf_s8_ld<2>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<2>(c, c.gP + o0 * c.ss, c.nP);
+        gf_s8_ld<2>(c, c.gI + o0 * c.gs, c.nI, c.sc[0]); gf_s8_ld<2>(c, c.gP + o0 * c.ss, c.nP, c.sc[1]);
         gf_s8_band<R, 2>(c, steps);
     } else if (mode == 3) {
-        gf_s8_ld<3>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<3>(c, c.gP + o0 * c.ss, c.nP);
+        gf_s8_ld<3>(c, c.gI + o0 * c.gs, c.nI, c.sc[0]); gf_s8_ld<3>(c, c.gP + o0 * c.ss, c.nP, c.sc[1]);
         gf_s8_band<R, 3>(c, steps);
     } else if (mode == 4) {
-        gf_s8_ld_row<4>(c, c.yi0, c.nI, c.nP);
+        gf_s8_ld_row<4>(c, c.yi0, c.nI, c.nP, c.sc[0], c.sc[1]);
         gf_s8_band<R, 4>(c, steps);
     } else {
-        gf_s8_ld<0>(c, c.gI + o0 * c.gs, c.nI); gf_s8_ld<0>(c, c.gP + o0 * c.ss, c.nP);
+        gf_s8_ld<0>(c, c.gI + o0 * c.gs, c.nI, c.sc[0]); gf_s8_ld<0>(c, c.gP + o0 * c.ss, c.nP, c.sc[1]);
         if constexpr (R == 8) {
             if (mode == 1) { gf_s8_band<R, 1>(c, steps); return; }
         }
@@ -737,8 +789,8 @@ static const char* gf_s8_launch(const Job& j)
     a.hb = hb;
     a.nbands = (j.out_rows + hb - 1) / hb;
     // The two edge strips run slower code (analytic edges at r = 8: +30 % instructions; mirror loads /
-    // clipped counts otherwise, ~1.8x the time per row): they get shorter bands, in proportion.  Measured on B200
-    // (profiles/r1_s8_edge_band_pct.txt): 4K r=16 125 -> 90 us, 8K r=32 780 -> 493 us, 4K r=8 66.2 -> 65.1 us.
+    // clipped counts otherwise, ~15 % more): they get shorter bands, in proportion.  Measured on B200
+    // (profiles/r1_s8_edge_band_pct.txt): 4K r=16 90.9 -> 85.7 us, 8K r=32 515 -> 483 us, 4K r=8 66.2 -> 65.1 us.
     int edge_pct = (R == 8 && j.border == GF_REFLECT101) ? GF_S8_EDGE_PCT_ANALYTIC : GF_S8_EDGE_PCT_OTHER;
     if (const char* e = getenv("GF_S8_EDGE_PCT")) edge_pct = atoi(e);
     a.hb_e = 0; a.nbands_e = 0;
