@@ -656,7 +656,11 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
     } else {
         band = (int)(idx / a.nstrips); strip = (int)(idx % a.nstrips); hbw = a.hb;
     }
+#ifdef GF_S8_NO_ANALYTIC_EDGE      // A/B switch: r = 8 edge strips by mirror loads (MODE 3) instead of the analytic mirror (MODE 1)
+    const bool edge_ok = false;
+#else
     const bool edge_ok = R == 8 && a.border == GF_REFLECT101 && (a.width & 7) == 0 && a.width >= G::WIN;
+#endif
     const bool first = strip == 0, last = strip == a.nstrips - 1;
 
     GfS8Ctx<R, T> c;
