@@ -262,16 +262,12 @@ __device__ __forceinline__ void gf_c4_band(GfC4Ctx<R>& c, int steps)
 }
 
 template <int R, int MINB>
-__global__ void __launch_bounds__(32, MINB) gf_c4_color_kernel(const GfWpArgs a)
+__global__ void __launch_bounds__(32, MINB) gf_c4_color_kernel(const GF_GRID_CONSTANT GfWpArgs a)
 {
     using G = GfC4Geom<R>;
     constexpr int M = G::M, VL = G::VL;
     GF_DYN_SMEM(float, smem);
-    const long item = (long)blockIdx.x;
-    const long per_frame = (long)a.nstrips * a.nbands;
-    const int64_t f = item / per_frame;
-    const int band = (int)((item % per_frame) / a.nstrips), strip = (int)(item % a.nstrips);
-
+    auto run = [&](int64_t f, int strip, int yo0, int yo1) {
     GfC4Ctx<R> c;
     c.lane = threadIdx.x & 31;
     const int xl = strip * G::WOUT - 2 * M * 4;
@@ -307,8 +303,6 @@ __global__ void __launch_bounds__(32, MINB) gf_c4_color_kernel(const GfWpArgs a)
         const int yl = a.buf_y0 + a.buf_rows - 1;
         c.buf_ylast = yl < a.height - 1 ? yl : a.height - 1;
     }
-    const int yo0 = a.out_y0 + band * a.hb;
-    const int yo1 = min(a.out_y0 + a.out_rows, yo0 + a.hb);
     c.yi0 = yo0 - 2 * R;
     c.eps = a.eps;
 #pragma unroll
@@ -332,6 +326,8 @@ __global__ void __launch_bounds__(32, MINB) gf_c4_color_kernel(const GfWpArgs a)
         gf_c4_load_row<R, false>(c, c.yi0, c.nI, c.nP);
         gf_c4_band<R, false>(c, steps);
     }
+    };
+    gf_tape_run(a, (long long)blockIdx.x, run);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -350,6 +346,7 @@ static const char* gf_c4_launch(const Job& j)
     a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
     a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
     a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
+    a.hb_e = 0; a.nbands_e = 0;
     const size_t smem = G::ring_bytes;
     constexpr int FIT = (int)((size_t)228 * 1024 / (G::ring_bytes + 1024));
     constexpr int MINB = FIT > 8 ? 8 : (FIT < 1 ? 1 : FIT);
@@ -361,7 +358,10 @@ static const char* gf_c4_launch(const Job& j)
     if (hb > j.out_rows) hb = j.out_rows;
     a.hb = hb;
     a.nbands = (j.out_rows + hb - 1) / hb;
-    const long items = (long)a.nstrips * a.nbands * j.count;
+    long items = (long)a.nstrips * a.nbands * j.count;
+    int we = 100;
+    if (const char* e = getenv("GF_C4_EDGE_WEIGHT")) we = atoi(e);
+    if (const long n = gf_tape_plan(a, R, (long)sms * warps_sm, 2 * R + 8, we)) items = n;
     dim3 grid((unsigned)items), block(32);
     auto k = gf_c4_color_kernel<R, MINB>;
     if (const char* e = gf_rt_set_smem(k, smem)) return e;

@@ -6,11 +6,13 @@
 // Test-only build (tests/emu): kernels compiled by g++ and run by the SIMT emulator.
 #include "cuda_emu.h"
 #define GF_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::dyn_smem())
+#define GF_GRID_CONSTANT
 #else
 #include <cuda_runtime.h>
 #define GF_DYN_SMEM(T, name)                                       \
     extern __shared__ __align__(16) unsigned char name##_raw_[];   \
     T* name = reinterpret_cast<T*>(name##_raw_)
+#define GF_GRID_CONSTANT __grid_constant__      // kernel parameters stay in the constant bank when referenced by address
 #endif
 
 // L2 prefetch hint (no registers, no scoreboard): rows a few iterations ahead of the loads.

@@ -21,10 +21,10 @@
 //     hinted into L2 a few rows further ahead;
 //   * the row loop is cut into phases with compile-time stage flags (straight-line steady state);
 //     the vertical border is a row-index map, the horizontal border (REFLECT/REFLECT101) is
-//     per-lane mapped loads in the first/last strip only (mirrored columns give mirrored a, b, so
-//     no other code changes).
-// TRUNCATE-border jobs, A/B outputs, unaligned planes and radii without an instantiation use the
-// older kernels (gf_wp.cuh, gf_fast.cuh, gf_generic.cuh).
+//     per-lane mirror loads in the first/last strip only (mirrored columns give mirrored a, b, so
+//     no other code changes); TRUNCATE zero-fills and divides by per-pixel counts.
+// A/B outputs, unaligned planes and radii without an instantiation use the older kernels
+// (gf_wp.cuh, gf_fast.cuh, gf_generic.cuh).
 #pragma once
 #include "gf_wp.cuh"
 
@@ -48,11 +48,8 @@
 #define GF_S8_SHFL_UP(v, d) __shfl_up_sync(0xffffffffu, v, d)
 #define GF_S8_SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, v, d)
 #endif
-#ifndef GF_S8_EDGE_PCT_ANALYTIC
-#define GF_S8_EDGE_PCT_ANALYTIC 78    // band height of the two edge strips, % of the interior strips' (r = 8, REFLECT101)
-#endif
-#ifndef GF_S8_EDGE_PCT_OTHER
-#define GF_S8_EDGE_PCT_OTHER 85       // ... for the other edge modes (mirror loads, clipped counts, column map)
+#ifndef GF_S8_EDGE_PCT
+#define GF_S8_EDGE_PCT 85     // band height of the two edge strips (mirror loads, clipped counts, column map), % of the interior strips'
 #endif
 #ifndef GF_S8_PF
 #define GF_S8_PF 4            // rows ahead for the L2 prefetch hint (0 = off)
@@ -165,19 +162,11 @@ __device__ __forceinline__ float2 gf_dup2(float a) { return make_float2(a, a); }
 // R a multiple of 8 (m = R/8): left term = suffix of lane l-m extended by the totals of lanes
 // l-m+1 .. l+m-1 (folded in at the SENDER: one chain of 8 additions), right term = prefix of lane
 // l+m.  Complete for lanes [m, 32-m).
-// EDGE (m = 1 only): lanes flagged `left` / `right` hold the first / last 8 columns of the image;
-// their missing neighbour is the REFLECT101 mirror image of columns the lane (and its inner
-// neighbour) already holds, so its prefix/suffix terms are formed locally, again by additions only:
-//   left :  A_j(-1)   = T(0) + (x_1 + .. + x_{8-j})            (x_8 = column 0 of lane 1 = r[0])
-//   right:  p_j(L+1)  = x_6 + x_5 + .. + x_{6-j}               (x_{-1} = column 7 of lane L-1)
-struct GfS8Edge { bool left, right; };
-
-template <int R, bool EDGE>
-__device__ __forceinline__ void gf_s8_window_m8(const float2 (&c)[4], float2 (&w)[4], const GfS8Edge eg)
+template <int R>
+__device__ __forceinline__ void gf_s8_window_m8(const float2 (&c)[4], float2 (&w)[4])
 {
     constexpr int M = R / 8;
     static_assert(R % 8 == 0 && M >= 1 && M <= 4, "folded window sum needs R = 8, 16, 24, 32");
-    static_assert(!EDGE || M == 1, "analytic image edges are implemented for R = 8 only");
     const float x[8] = {c[0].x, c[0].y, c[1].x, c[1].y, c[2].x, c[2].y, c[3].x, c[3].y};
     // Prefixes and extended suffixes as shallow trees (dependency depth 4 instead of 8): the serial
     // chains left the warp waiting on FADD latency; the 4 extra additions per quantity are free.
@@ -204,35 +193,16 @@ __device__ __forceinline__ void gf_s8_window_m8(const float2 (&c)[4], float2 (&w
 #pragma unroll
     for (int j = 0; j < 7; ++j) r[j] = GF_S8_SHFL_DOWN(p[j], M);
     r[7] = tn[M];
-    if (EDGE) {
-        const float x7m = GF_S8_SHFL_UP(x[7], 1);
-        float pp[8];                                   // pp[n] = x_1 + .. + x_n
-        pp[1] = x[1]; pp[2] = x[1] + x[2]; pp[3] = x[1] + t23;
-        pp[4] = pp[3] + x[4]; pp[5] = pp[3] + t45; pp[6] = pp[5] + x[6]; pp[7] = pp[5] + t67;
-        float lv[8], rv[8];
-        lv[0] = (p[7] + pp[7]) + r[0];
-#pragma unroll
-        for (int j = 1; j < 8; ++j) lv[j] = p[7] + pp[8 - j];
-        rv[0] = x[6]; rv[1] = x[6] + x[5]; rv[2] = x[6] + t45;
-        rv[3] = rv[2] + x[3]; rv[4] = rv[2] + t23; rv[5] = rv[4] + x[1]; rv[6] = rv[4] + t01;
-        rv[7] = rv[6] + x7m;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            l[j] = eg.left ? lv[j] : l[j];
-            r[j] = eg.right ? rv[j] : r[j];
-        }
-    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) w[i] = gf_add2(make_float2(l[2 * i], l[2 * i + 1]), make_float2(r[2 * i], r[2 * i + 1]));
 }
 
-template <int R, bool EDGE>
-__device__ __forceinline__ void gf_s8_window(const float2 (&c)[4], float2 (&w)[4], int lane, const GfS8Edge eg)
+template <int R>
+__device__ __forceinline__ void gf_s8_window(const float2 (&c)[4], float2 (&w)[4], int lane)
 {
     if constexpr (R % 8 == 0) {
-        gf_s8_window_m8<R, EDGE>(c, w, eg);
+        gf_s8_window_m8<R>(c, w);
     } else {
-        static_assert(!EDGE, "analytic image edges need R = 8");
         const float x[8] = {c[0].x, c[0].y, c[1].x, c[1].y, c[2].x, c[2].y, c[3].x, c[3].y};
         float o[8];
         gf_window_k<R, 8>(x, o, lane);
@@ -260,7 +230,6 @@ struct GfS8Ctx {
     float2* ring;                                    // this lane's cell of ring row 0
     int lane, x0, width, height, border, buf_y0, buf_ylast, out_y0, yi0;
     bool vec_ok, ring_lane, out_lane;
-    GfS8Edge edge;                                   // MODE 1 only
     bool out_l, out_r;                               // MODE 3 only: lane lies left / right of the image
     int vofs, sofs;                                  // MODE 3 only: vector / scalar source offsets relative to x0
     bool lane_in;                                    // MODE 4 only: this lane's 8 columns lie inside the image
@@ -294,7 +263,7 @@ __device__ __forceinline__ float gf_s8_rcp(float d)
 #endif
 }
 
-// Strip modes: 0 interior; 1 analytic REFLECT101 image edges (R = 8); 3 mirror loads -- REFLECT101,
+// Strip modes: 0 interior; 3 mirror loads -- REFLECT101,
 // width % 8 == 0: a lane that lies outside the image reads the aligned 8-column group that holds
 // 7 of its 8 mirror columns plus one scalar, and permutes at compile time (no per-column gather);
 // 2 generic per-column border map (any border, any width; slow, rarely needed); 4 TRUNCATE border
@@ -418,7 +387,7 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R, T>& c, int t, int slot, bo
 {
     using G = GfS8Geom<R>;
     constexpr int KW = G::KW, VL = G::VL;
-    constexpr bool XMAP = MODE == 2, EDGE = MODE == 1;
+    constexpr bool XMAP = MODE == 2;
     const int yi = c.yi0 + t;
     const int lane = c.lane;
 
@@ -464,8 +433,8 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R, T>& c, int t, int slot, bo
     // ================= phase A: stage 2 of centre row yi-1-R (guide row of its output: gI) =================
     {
         float2 hA[4], hB[4];
-        gf_s8_window<R, EDGE>(c.va, hA, lane, c.edge);
-        gf_s8_window<R, EDGE>(c.vb, hB, lane, c.edge);
+        gf_s8_window<R>(c.va, hA, lane);
+        gf_s8_window<R>(c.vb, hB, lane);
         if (c.ring_lane && !(GF_S8_ABL & 2)) {
             float2* s = c.ring + slot * G::SLOT_F2;
             if (full) {
@@ -525,10 +494,10 @@ __device__ __forceinline__ void gf_s8_iter(GfS8Ctx<R, T>& c, int t, int slot, bo
         // horizontal -> a, b of row yi - R.  Every window is full (REFLECT borders mirror the data):
         //   a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2),   b = (S_p - a S_I) / N
         float2 hI[4], hP[4], hIP[4], hII[4];
-        gf_s8_window<R, EDGE>(c.cI, hI, lane, c.edge);
-        gf_s8_window<R, EDGE>(c.cP, hP, lane, c.edge);
-        gf_s8_window<R, EDGE>(c.cIP, hIP, lane, c.edge);
-        gf_s8_window<R, EDGE>(c.cII, hII, lane, c.edge);
+        gf_s8_window<R>(c.cI, hI, lane);
+        gf_s8_window<R>(c.cP, hP, lane);
+        gf_s8_window<R>(c.cIP, hIP, lane);
+        gf_s8_window<R>(c.cII, hII, lane);
         if (MODE == 4) {
             // TRUNCATE: N = (in-image columns) x (in-image rows) of the window of (x, yc); a, b are zero outside the image
             const int yc = yi - R;
@@ -627,67 +596,34 @@ __device__ __forceinline__ void gf_s8_band(GfS8Ctx<R, T>& c, int steps)
     }
 }
 
-// Strip geometry.  edge_ok (R = 8, REFLECT101, width % 8 == 0, width >= 256): the first strip
-// starts at column 0 and the last one ends at the last column, their image-side lanes use the
-// analytic mirror (MODE 1) and all their lanes on that side produce output.  Otherwise strips
-// that overhang the image use mirror loads (MODE 3: REFLECT101, width % 8 == 0) or the generic
-// per-column border map (MODE 2).
+// Strip geometry: strip s outputs columns [s * WOUT, (s + 1) * WOUT) and reads 2 * H1 lanes of halo
+// on either side.  Strips that overhang the image use mirror loads (MODE 3: REFLECT101,
+// width % 8 == 0), clipped counts (MODE 4: TRUNCATE) or the generic per-column border map (MODE 2).
 template <int R, int MINB, class T>
-__global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
+__global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GF_GRID_CONSTANT GfWpArgs a)
 {
     using G = GfS8Geom<R>;
     constexpr int H1 = G::H1, KW = G::KW, VL = G::VL;
     GF_DYN_SMEM(float, smem);
-    const long item = (long)blockIdx.x;
-    // Work items of a frame: the first and the last strip (slower code: image edges) come first and in
-    // nbands_e bands of hb_e rows, the interior strips follow in nbands bands of hb rows -- so that all
-    // warps of the single wave finish together (the kernel is as slow as its slowest warp).
-    const bool two = a.nbands_e > 0 && a.nstrips >= 3;
-    const long n_edge = two ? 2L * a.nbands_e : 0, n_int = two ? (long)(a.nstrips - 2) * a.nbands : (long)a.nstrips * a.nbands;
-    const long per_frame = n_edge + n_int;
-    const int64_t f = item / per_frame;
-    const long idx = item % per_frame;
-    int band, strip, hbw;
-    if (idx < n_edge) {
-        band = (int)(idx >> 1); strip = (idx & 1) ? a.nstrips - 1 : 0; hbw = a.hb_e;
-    } else if (two) {
-        const long k = idx - n_edge;
-        band = (int)(k / (a.nstrips - 2)); strip = 1 + (int)(k % (a.nstrips - 2)); hbw = a.hb;
-    } else {
-        band = (int)(idx / a.nstrips); strip = (int)(idx % a.nstrips); hbw = a.hb;
-    }
-#ifdef GF_S8_NO_ANALYTIC_EDGE      // A/B switch: r = 8 edge strips by mirror loads (MODE 3) instead of the analytic mirror (MODE 1)
-    const bool edge_ok = false;
-#else
-    const bool edge_ok = R == 8 && a.border == GF_REFLECT101 && (a.width & 7) == 0 && a.width >= G::WIN;
-#endif
-    const bool first = strip == 0, last = strip == a.nstrips - 1;
-
+    auto run = [&](int64_t f, int strip, int yo0, int yo1) {
     GfS8Ctx<R, T> c;
     c.lane = threadIdx.x & 31;
-    int xl = strip * G::WOUT - 2 * H1 * 8, lane_lo = 2 * H1, col_min = 0;
+    const int xl = strip * G::WOUT - 2 * H1 * 8, lane_lo = 2 * H1;
     int mode = 0;
-    if (edge_ok && (first || last)) {
-        mode = 1;
-        if (first) { xl = 0; lane_lo = 0; }
-        if (last && !first) { xl = a.width - G::WIN; lane_lo = 4 * H1; col_min = strip * G::WOUT; }
-    } else if (a.border == GF_TRUNCATE) {
+    if (a.border == GF_TRUNCATE) {
         // interior warps (every window they touch is full) run the plain code; the others count pixels
-        const int by0 = a.out_y0 + band * hbw, by1 = min(a.out_y0 + a.out_rows, by0 + hbw);
-        const bool inside = xl >= 0 && xl + G::WIN <= a.width && by0 - 2 * R >= 0 && by1 + 2 * R <= a.height;
+        const bool inside = xl >= 0 && xl + G::WIN <= a.width && yo0 - 2 * R >= 0 && yo1 + 2 * R <= a.height;
         mode = inside ? 0 : 4;
     } else if (xl < 0 || xl + G::WIN > a.width) {
         mode = (a.border == GF_REFLECT101 && (a.width & 7) == 0 && a.width >= G::WIN) ? 3 : 2;
     }
     c.x0 = xl + 8 * c.lane;
-    c.edge.left = mode == 1 && first && c.lane == 0;
-    c.edge.right = mode == 1 && last && c.x0 + 8 == a.width;
     // (GfWpArgs carries the planes as float*; T = unsigned char builds reinterpret them, strides are in elements)
     c.gI = reinterpret_cast<const T*>(a.guide) + f * a.gfs + c.x0; c.gP = reinterpret_cast<const T*>(a.src) + f * a.sfs + c.x0;
     c.gQ = reinterpret_cast<T*>(a.dst) + f * a.dfs + c.x0;
     c.gs = (int)a.gs; c.ss = (int)a.ss; c.ds = (int)a.ds;
     c.ring_lane = c.lane >= lane_lo && c.lane < lane_lo + VL;
-    c.out_lane = c.ring_lane && c.x0 < a.width && c.x0 >= col_min;
+    c.out_lane = c.ring_lane && c.x0 < a.width;
     c.ring = reinterpret_cast<float2*>(smem) + (c.ring_lane ? c.lane - lane_lo : 0);
     c.width = a.width; c.height = a.height; c.border = a.border; c.buf_y0 = a.buf_y0; c.out_y0 = a.out_y0;
     {
@@ -703,8 +639,6 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
     c.out_r = mode == 3 && c.x0 >= a.width;
     c.vofs = c.out_l ? -2 * c.x0 - 8 : (c.out_r ? 2 * a.width - 8 - 2 * c.x0 : 0);
     c.sofs = c.out_l ? -2 * c.x0 : (c.out_r ? 2 * a.width - 9 - 2 * c.x0 : 0);
-    const int yo0 = a.out_y0 + band * hbw;
-    const int yo1 = min(a.out_y0 + a.out_rows, yo0 + hbw);
     c.yi0 = yo0 - 2 * R;
     c.eps = sizeof(T) == 4 ? a.eps : a.eps * 65025.0f;      // uint8 build: integer domain, eps scales with 255^2
     c.nk = gf_norm_make((float)(KW * KW));
@@ -731,11 +665,10 @@ __global__ void __launch_bounds__(32, MINB) gf_s8_gray_kernel(const GfWpArgs a)
         gf_s8_band<R, 4>(c, steps);
     } else {
         gf_s8_ld<0>(c, c.gI + o0 * c.gs, c.nI, c.sc[0]); gf_s8_ld<0>(c, c.gP + o0 * c.ss, c.nP, c.sc[1]);
-        if constexpr (R == 8) {
-            if (mode == 1) { gf_s8_band<R, 1>(c, steps); return; }
-        }
         gf_s8_band<R, 0>(c, steps);
     }
+    };
+    gf_tape_run(a, (long long)blockIdx.x, run);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -758,6 +691,24 @@ static inline int gf_pick_band_rows(int rows, int r, long nstrips_x_count, long 
         if (cost < best * 0.999) { best = cost; best_hb = hb; }
     }
     return best_hb;
+}
+
+// Tape plan (gf_tape_run in gf_wp.cuh): fills a.tape_* and returns the grid size (one 1-warp CTA per
+// piece, at most `slots` so that the job is one wave; pieces are at least hb_min rows + one ramp long).
+// GF_TAPE=0 in the environment selects the uniform split (A/B and fallback).
+static inline long gf_tape_plan(GfWpArgs& a, int r, long slots, int hb_min, int we_pct)
+{
+    a.tape_piece = 0; a.tape_rho = (int)(2.3 * r + 1.0); a.tape_we = we_pct < 100 ? 100 : we_pct;
+    if (const char* e = getenv("GF_TAPE")) if (atoi(e) == 0) return 0;
+    const bool edges = a.nstrips >= 3 && a.tape_we != 100;
+    const long long zi = (long long)(a.tape_rho + a.out_rows) * 100, ze = (long long)(a.tape_rho + a.out_rows) * a.tape_we;
+    const long long total = (edges ? 2 * ze + (a.nstrips - 2) * zi : a.nstrips * zi) * a.count;
+    const long long min_piece = (long long)(hb_min + a.tape_rho) * 100;
+    long long n = total / min_piece;
+    if (n > slots) n = slots;
+    if (n < 1) n = 1;
+    a.tape_piece = (total + n - 1) / n;
+    return (long)((total + a.tape_piece - 1) / a.tape_piece);
 }
 
 template <int R, class T = float>
@@ -792,10 +743,10 @@ static const char* gf_s8_launch(const Job& j)
     if (hb > j.out_rows) hb = j.out_rows;
     a.hb = hb;
     a.nbands = (j.out_rows + hb - 1) / hb;
-    // The two edge strips run slower code (analytic edges at r = 8: +30 % instructions; mirror loads /
-    // clipped counts otherwise, ~15 % more): they get shorter bands, in proportion.  Measured on B200
+    // The two edge strips run slower code (mirror loads / clipped counts, ~15 % more instructions):
+    // they get shorter bands, in proportion.  Measured on B200
     // (profiles/r1_s8_edge_band_pct.txt): 4K r=16 90.9 -> 85.7 us, 8K r=32 515 -> 483 us, 4K r=8 66.2 -> 65.1 us.
-    int edge_pct = (R == 8 && j.border == GF_REFLECT101) ? GF_S8_EDGE_PCT_ANALYTIC : GF_S8_EDGE_PCT_OTHER;
+    int edge_pct = GF_S8_EDGE_PCT;
     if (const char* e = getenv("GF_S8_EDGE_PCT")) edge_pct = atoi(e);
     a.hb_e = 0; a.nbands_e = 0;
     if (a.nstrips >= 3 && edge_pct > 0 && edge_pct < 100 && a.nbands > 1) {
@@ -815,7 +766,9 @@ static const char* gf_s8_launch(const Job& j)
         a.nbands = (j.out_rows + hb - 1) / hb;
     }
     const long per_frame = a.nbands_e > 0 ? 2L * a.nbands_e + (long)(a.nstrips - 2) * a.nbands : (long)a.nstrips * a.nbands;
-    const long items = per_frame * j.count;
+    long items = per_frame * j.count;
+    if (!getenv("GF_S8_HB"))
+        if (const long n = gf_tape_plan(a, R, (long)sms * warps_sm, hb_min, edge_pct > 0 && edge_pct < 100 ? 10000 / edge_pct : 100)) items = n;
     dim3 grid((unsigned)items), block(32);
     constexpr int FIT = (int)((size_t)228 * 1024 / (G::ring_bytes + 1024));
     constexpr int MINB = FIT > 7 ? 7 : (FIT < 1 ? 1 : FIT);

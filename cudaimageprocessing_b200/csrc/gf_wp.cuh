@@ -127,7 +127,69 @@ struct GfWpArgs {
     int nstrips, nbands, count;
     int hb_e, nbands_e;      // gf_s8 only: band height / band count of the first and last strip (0 = same as the others)
     float eps;
+    // Tape scheduling (gf_s8 / gf_c4, tape_piece > 0; see gf_tape_run): one CTA per piece of the tape
+    long long tape_piece;    // piece length in cost units (a row of an interior strip = 100 units)
+    int tape_rho, tape_we;   // ramp of a band in rows; cost of a row of the first / last strip (>= 100)
 };
+
+// Tape scheduling.  The uniform split (nbands bands of hb rows per strip) leaves the machine badly
+// filled whenever strips x bands is not just below a multiple of the resident warps (32 frames of
+// 1080p colour, r = 16: 960 strips on 888 warp slots -> 3 waves of half-height bands, 33 % ramp).
+// Instead all (frame, strip) columns are laid end to end on a tape, every column preceded by the
+// cost of one ramp (rho rows: the 4R warm-up iterations of a band cost about 2.3R + 1 row times),
+// rows of the first and last strip weighted by their slower code, and the tape is cut into equal
+// pieces, one per resident warp.  A warp walks its piece: every column it touches is one band
+// (its own ramp + its rows), so every warp does the same work to within one row and the whole job
+// is ONE wave:   time ~ tape / slots + ramp   instead of   waves x (hb + ramp).
+// body(frame, strip, first output row, end output row) runs one band.
+// With tape_piece == 0 the item is one band of the uniform split: per frame the first and the last
+// strip come first in nbands_e bands of hb_e rows (nbands_e > 0, nstrips >= 3: gf_s8's shorter bands
+// for the slower edge code), the other strips follow in nbands bands of hb rows.
+template <class F>
+__device__ __forceinline__ void gf_tape_run(const GfWpArgs& a, long long item, F&& body)
+{
+    const bool tape = a.tape_piece > 0;
+    const int rho = a.tape_rho, we = a.tape_we, ns = a.nstrips;
+    const bool edges = ns >= 3 && we != 100;
+    const long long zi = (long long)(rho + a.out_rows) * 100, ze = (long long)(rho + a.out_rows) * we;
+    const long long frame = edges ? 2 * ze + (ns - 2) * zi : ns * zi;
+    long long pos = tape ? item * a.tape_piece : 0;
+    long long end = tape ? pos + a.tape_piece : 1;
+    if (tape && end > frame * a.count) end = frame * a.count;
+    while (pos < end) {
+        int64_t f;
+        int strip, r0, r1;
+        if (tape) {
+            const long long fb = (pos / frame) * frame, rem = pos - fb;
+            f = pos / frame;
+            int w;
+            long long z0;
+            if (!edges) { strip = (int)(rem / zi); z0 = strip * zi; w = 100; }
+            else if (rem < ze) { strip = 0; z0 = 0; w = we; }
+            else if (rem < ze + (ns - 2) * zi) { const int k = (int)((rem - ze) / zi); strip = 1 + k; z0 = ze + k * zi; w = 100; }
+            else { strip = ns - 1; z0 = ze + (ns - 2) * zi; w = we; }
+            const long long zlen = (long long)(rho + a.out_rows) * w, lead = (long long)rho * w;
+            const long long u0 = rem - z0, u1 = end - fb - z0 < zlen ? end - fb - z0 : zlen;
+            // first row whose cost interval starts at or after u: pieces tile every column exactly
+            r0 = u0 <= lead ? 0 : (int)((u0 - lead + w - 1) / w);
+            r1 = u1 <= lead ? 0 : (int)((u1 - lead + w - 1) / w);
+            pos = fb + z0 + zlen;
+        } else {
+            const bool two = a.nbands_e > 0 && ns >= 3;
+            const long n_edge = two ? 2L * a.nbands_e : 0, n_int = two ? (long)(ns - 2) * a.nbands : (long)ns * a.nbands;
+            const long per_frame = n_edge + n_int, idx = (long)(item % per_frame);
+            f = item / per_frame;
+            int band, hbw;
+            if (idx < n_edge) { band = (int)(idx >> 1); strip = (idx & 1) ? ns - 1 : 0; hbw = a.hb_e; }
+            else if (two) { const long k = idx - n_edge; band = (int)(k / (ns - 2)); strip = 1 + (int)(k % (ns - 2)); hbw = a.hb; }
+            else { band = (int)(idx / ns); strip = (int)(idx % ns); hbw = a.hb; }
+            r0 = band * hbw;
+            r1 = r0 + hbw < a.out_rows ? r0 + hbw : a.out_rows;
+            pos = end;
+        }
+        if (r1 > r0) body(f, strip, a.out_y0 + r0, a.out_y0 + r1);
+    }
+}
 
 template <int R, int K>
 struct GfWpCtx {
@@ -408,6 +470,7 @@ static const char* gf_wp_launch(const Job& j)
     a.gfs = j.guide.frame_stride; a.sfs = j.src.frame_stride; a.dfs = j.dst.frame_stride; a.abfs = j.A.frame_stride;
     a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
     a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
+    a.hb_e = 0; a.nbands_e = 0; a.tape_piece = 0; a.tape_rho = 0; a.tape_we = 100;
     a.nstrips = (j.width + W::WOUT - 1) / W::WOUT;
     const size_t smem = W::WARPS * W::ring_bytes_per_warp;
     // resident warps per SM: shared memory (ring) and registers (<= 168 per thread at 12 warps)
