@@ -1,5 +1,5 @@
 """Developer tool (GPU box): tape scheduling (default) vs the uniform band split (GF_TAPE=0).
-Checks that both give bit-identical output and times both on gray / colour / batch / giga cases."""
+Reports the difference of the two outputs (last-bit: re-seed phases differ) and times both on gray / colour / batch / giga cases."""
 import ctypes, json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -46,7 +46,7 @@ def gray(w, h, r, border=0, iters=40, nsets=4):
         torch.cuda.synchronize()
         res[tag + "_us"] = round(ms * 1e3, 2); res[tag + "_kernel"] = api.last_kernel()
         clrenv(env)
-    res["identical"] = bool(torch.equal(q[0], q[1])); res["nan"] = int(torch.isnan(q[1]).sum())
+    res["max_diff"] = float((q[0] - q[1]).abs().max()); res["nan"] = int(torch.isnan(q[1]).sum())
     res["gain_pct"] = round(100 * (1 - res["tape_us"] / res["uniform_us"]), 1)
     print(json.dumps(res), flush=True)
 
@@ -62,7 +62,7 @@ def color(n, w, h, r, iters=5, extra=None):
         ms = timed(f, iters)
         res[tag + "_ms"] = round(ms, 4); res[tag + "_kernel"] = api.last_kernel()
         clrenv(env)
-    res["identical"] = bool(torch.equal(q[0], q[1])); res["nan"] = int(torch.isnan(q[1]).sum())
+    res["max_diff"] = float((q[0] - q[1]).abs().max()); res["nan"] = int(torch.isnan(q[1]).sum())
     res["gain_pct"] = round(100 * (1 - res["tape_ms"] / res["uniform_ms"]), 1)
     print(json.dumps(res), flush=True)
     del I, p, q

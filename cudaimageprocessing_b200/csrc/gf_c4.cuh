@@ -361,7 +361,8 @@ static const char* gf_c4_launch(const Job& j)
     long items = (long)a.nstrips * a.nbands * j.count;
     int we = 100;
     if (const char* e = getenv("GF_C4_EDGE_WEIGHT")) we = atoi(e);
-    if (const long n = gf_tape_plan(a, R, (long)sms * warps_sm, 2 * R + 8, we)) items = n;
+    if (!getenv("GF_C4_HB"))
+        if (const long n = gf_tape_plan(a, R, (long)sms * warps_sm, 2 * R + 8, we)) items = n;
     dim3 grid((unsigned)items), block(32);
     auto k = gf_c4_color_kernel<R, MINB>;
     if (const char* e = gf_rt_set_smem(k, smem)) return e;

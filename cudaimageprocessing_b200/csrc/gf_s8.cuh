@@ -700,6 +700,7 @@ static inline long gf_tape_plan(GfWpArgs& a, int r, long slots, int hb_min, int 
 {
     a.tape_piece = 0; a.tape_rho = (int)(2.3 * r + 1.0); a.tape_we = we_pct < 100 ? 100 : we_pct;
     if (const char* e = getenv("GF_TAPE")) if (atoi(e) == 0) return 0;
+    if (const char* e = getenv("GF_TAPE_SLOTS")) slots = atol(e);       // tests / experiments: pieces that span several strips
     const bool edges = a.nstrips >= 3 && a.tape_we != 100;
     const long long zi = (long long)(a.tape_rho + a.out_rows) * 100, ze = (long long)(a.tape_rho + a.out_rows) * a.tape_we;
     const long long total = (edges ? 2 * ze + (a.nstrips - 2) * zi : a.nstrips * zi) * a.count;

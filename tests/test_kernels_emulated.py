@@ -213,6 +213,45 @@ def test_gray_s8_two_band_classes(be, shape, r, border, monkeypatch):
     assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
 
 
+@pytest.mark.parametrize("shape,r,border,slots,pct", [((90, 1000), 8, 0, 1036, 85), ((90, 1000), 8, 0, 7, 85), ((90, 1000), 8, 0, 3, 60),
+                                                      ((60, 704), 4, 1, 11, 85), ((75, 520), 7, 2, 5, 85), ((64, 256), 8, 0, 4, 85),
+                                                      ((100, 640), 16, 0, 6, 70), ((41, 1000), 8, 0, 1, 85)])
+def test_gray_s8_tape(be, shape, r, border, slots, pct, monkeypatch):
+    """tape scheduling (gf_tape_run): pieces shorter than a strip, pieces that cross strips, pieces that
+    span several strips (few slots), weighted edge strips, one piece for the whole job.  (The uniform
+    split differs in the last bits only: the running sums are re-seeded relative to the band start.)"""
+    monkeypatch.setenv("GF_TAPE_SLOTS", str(slots))
+    monkeypatch.setenv("GF_S8_EDGE_PCT", str(pct))
+    I, p = synth_pair(*shape, seed=75, kind="structured")
+    q = be.guided_gray(I, p, r, 1e-2, border)
+    assert be.api.last_kernel() == f"s8_r{r}"
+    assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
+    monkeypatch.setenv("GF_TAPE", "0")
+    q0 = be.guided_gray(I, p, r, 1e-2, border)
+    assert np.abs(q - q0).max() <= 2e-6
+
+
+def test_tape_batch(be, monkeypatch):
+    """pieces that cross from one frame into the next (gray and colour batches)"""
+    rng = np.random.default_rng(18)
+    monkeypatch.setenv("GF_TAPE_SLOTS", "5")
+    Ib = rng.random((3, 40, 480), dtype=np.float32)
+    pb = rng.random((3, 40, 480), dtype=np.float32)
+    qb = be.batch(Ib, pb, 8, 1e-2, 0)
+    assert be.api.last_kernel() == "s8_r8"
+    for k in range(3):
+        assert np.abs(qb[k] - O.guided_filter_gray(Ib[k], pb[k], 8, 1e-2, 0)).max() <= TOL
+    I = rng.random((3, 40, 160, 3), dtype=np.float32)
+    p = rng.random((3, 40, 160), dtype=np.float32)
+    for slots, we in ((5, 100), (2, 125)):
+        monkeypatch.setenv("GF_TAPE_SLOTS", str(slots))
+        monkeypatch.setenv("GF_C4_EDGE_WEIGHT", str(we))
+        q = be.batch(I, p, 8, 1e-2, 0)
+        assert be.api.last_kernel() == "c4_r8"
+        for k in range(3):
+            assert np.abs(q[k] - O.guided_filter_color(I[k], p[k], 8, 1e-2, 0)).max() <= TOL
+
+
 def test_gray_s8_batch_strip_kat(be):
     rng = np.random.default_rng(8)
     Ib = rng.random((2, 40, 320), dtype=np.float32)
