@@ -1,4 +1,4 @@
-"""Developer tool (GPU box): tape scheduling (default) vs the uniform band split (GF_TAPE=0).
+"""Developer tool (GPU box): tape scheduling (GF_TAPE=1) vs the uniform band split (default).
 Reports the difference of the two outputs (last-bit: re-seed phases differ) and times both on gray / colour / batch / giga cases."""
 import ctypes, json, os, sys
 import torch
@@ -33,7 +33,7 @@ def gray(w, h, r, border=0, iters=40, nsets=4):
     sets = [(torch.rand((h, w), device="cuda", generator=g), torch.rand((h, w), device="cuda", generator=g)) for _ in range(nsets)]
     q = [torch.full((h, w), float("nan"), device="cuda") for _ in range(2)]
     res = {"case": f"gray {w}x{h} r={r} border={border}"}
-    for tag, env in (("tape", {}), ("uniform", {"GF_TAPE": 0})):
+    for tag, env in (("tape", {"GF_TAPE": 1}), ("uniform", {"GF_TAPE": 0})):
         setenv(env)
         i = [0]
         def f():
@@ -56,7 +56,7 @@ def color(n, w, h, r, iters=5, extra=None):
     I = torch.rand((n, h, w, 3), device="cuda", generator=g); p = torch.rand((n, h, w), device="cuda", generator=g)
     q = [torch.full((n, h, w), float("nan"), device="cuda") for _ in range(2)]
     res = {"case": f"colour {n}x{w}x{h} r={r}", "extra": extra or {}}
-    for tag, env in (("tape", dict(extra or {})), ("uniform", {"GF_TAPE": 0})):
+    for tag, env in (("tape", dict(extra or {}, GF_TAPE=1)), ("uniform", {"GF_TAPE": 0})):
         setenv(env)
         f = lambda: api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q[tag == "tape"].data_ptr(), n, w, h, 3, 0, 0, 0, 0, 0, 0, r, 1e-2, 0, sp)
         ms = timed(f, iters)

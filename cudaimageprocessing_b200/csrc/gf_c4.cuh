@@ -345,6 +345,7 @@ static const char* gf_c4_launch(const Job& j)
     a.gfs = j.guide.frame_stride; a.sfs = j.src.frame_stride; a.dfs = j.dst.frame_stride; a.abfs = 0;
     a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
     a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
+    a.tape_piece = 0; a.tape_rho = 0; a.tape_we = 100;
     a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
     a.hb_e = 0; a.nbands_e = 0;
     const size_t smem = G::ring_bytes;

@@ -695,11 +695,16 @@ static inline int gf_pick_band_rows(int rows, int r, long nstrips_x_count, long 
 
 // Tape plan (gf_tape_run in gf_wp.cuh): fills a.tape_* and returns the grid size (one 1-warp CTA per
 // piece, at most `slots` so that the job is one wave; pieces are at least hb_min rows + one ramp long).
-// GF_TAPE=0 in the environment selects the uniform split (A/B and fallback).
+// EXPERIMENT, off unless GF_TAPE=1: on B200 it measured 2-25 % SLOWER than the uniform split on
+// every gray case and on large colour batches, and only 3-8 % faster on 16-32 frame colour batches
+// (profiles/r1_tape_scheduling_ab.jsonl, profiles/r1_c4_band_sweep.jsonl): pieces of neighbouring
+// strips no longer walk the same rows at the same time, so the strip halos stop hitting in L2, and
+// a piece that crosses into the next strip pays a second ramp that costs more than the model says.
 static inline long gf_tape_plan(GfWpArgs& a, int r, long slots, int hb_min, int we_pct)
 {
     a.tape_piece = 0; a.tape_rho = (int)(2.3 * r + 1.0); a.tape_we = we_pct < 100 ? 100 : we_pct;
-    if (const char* e = getenv("GF_TAPE")) if (atoi(e) == 0) return 0;
+    const char* on = getenv("GF_TAPE");
+    if (!on || atoi(on) == 0) return 0;
     if (const char* e = getenv("GF_TAPE_SLOTS")) slots = atol(e);       // tests / experiments: pieces that span several strips
     const bool edges = a.nstrips >= 3 && a.tape_we != 100;
     const long long zi = (long long)(a.tape_rho + a.out_rows) * 100, ze = (long long)(a.tape_rho + a.out_rows) * a.tape_we;
@@ -726,6 +731,7 @@ static const char* gf_s8_launch(const Job& j)
     a.gfs = j.guide.frame_stride; a.sfs = j.src.frame_stride; a.dfs = j.dst.frame_stride; a.abfs = 0;
     a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
     a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
+    a.tape_piece = 0; a.tape_rho = 0; a.tape_we = 100;
     a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
     size_t smem = G::ring_bytes;
     if (const char* e = getenv("GF_S8_EXTRA_SMEM")) smem += (size_t)atoi(e);      // experiments: lower the residency

@@ -132,7 +132,7 @@ struct GfWpArgs {
     int tape_rho, tape_we;   // ramp of a band in rows; cost of a row of the first / last strip (>= 100)
 };
 
-// Tape scheduling.  The uniform split (nbands bands of hb rows per strip) leaves the machine badly
+// Tape scheduling (experiment, off by default: see gf_tape_plan for the measured outcome).  The uniform split (nbands bands of hb rows per strip) leaves the machine badly
 // filled whenever strips x bands is not just below a multiple of the resident warps (32 frames of
 // 1080p colour, r = 16: 960 strips on 888 warp slots -> 3 waves of half-height bands, 33 % ramp).
 // Instead all (frame, strip) columns are laid end to end on a tape, every column preceded by the

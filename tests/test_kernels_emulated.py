@@ -220,6 +220,7 @@ def test_gray_s8_tape(be, shape, r, border, slots, pct, monkeypatch):
     """tape scheduling (gf_tape_run): pieces shorter than a strip, pieces that cross strips, pieces that
     span several strips (few slots), weighted edge strips, one piece for the whole job.  (The uniform
     split differs in the last bits only: the running sums are re-seeded relative to the band start.)"""
+    monkeypatch.setenv("GF_TAPE", "1")
     monkeypatch.setenv("GF_TAPE_SLOTS", str(slots))
     monkeypatch.setenv("GF_S8_EDGE_PCT", str(pct))
     I, p = synth_pair(*shape, seed=75, kind="structured")
@@ -234,6 +235,7 @@ def test_gray_s8_tape(be, shape, r, border, slots, pct, monkeypatch):
 def test_tape_batch(be, monkeypatch):
     """pieces that cross from one frame into the next (gray and colour batches)"""
     rng = np.random.default_rng(18)
+    monkeypatch.setenv("GF_TAPE", "1")
     monkeypatch.setenv("GF_TAPE_SLOTS", "5")
     Ib = rng.random((3, 40, 480), dtype=np.float32)
     pb = rng.random((3, 40, 480), dtype=np.float32)
