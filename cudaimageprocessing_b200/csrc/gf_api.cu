@@ -15,6 +15,7 @@
 #include "gf_job.h"
 #include "gf_pointwise.cuh"
 #include "gf_integral.cuh"
+#include "gf_gauss.cuh"
 #include "gf_rt.h"
 #ifdef GF_HAVE_FAST
 #include "gf_fast.cuh"
@@ -325,6 +326,24 @@ int gf_integral_u8_i32_padded(const unsigned char* src, int32_t* integral, int s
 {
     return integral_entry<int32_t>(src, integral, nullptr, src_width, src_height, dst_width, dst_height, src_stride, dst_width, stream,
                                    "gf_integral_u8_i32_padded");
+}
+
+int gf_gaussian_gray(const float* src, float* dst, int width, int height, int64_t src_stride, int64_t dst_stride, int radius,
+                     double sigma, void* stream)
+{
+    if (!src || !dst) return fail(GF_ERR_INVALID, "gf_gaussian_gray: null pointer");
+    if (src == dst) return fail(GF_ERR_INVALID, "gf_gaussian_gray: in-place filtering is not supported");
+    if (width <= 0 || height <= 0) return fail(GF_ERR_INVALID, "gf_gaussian_gray: bad size %dx%d", width, height);
+    if (radius < 0 || radius > GF_GAUSS_MAX_R) return fail(GF_ERR_INVALID, "gf_gaussian_gray: radius %d outside [0, %d]", radius, GF_GAUSS_MAX_R);
+    if (src_stride <= 0) src_stride = width;
+    if (dst_stride <= 0) dst_stride = width;
+    if (src_stride < width || dst_stride < width) return fail(GF_ERR_INVALID, "gf_gaussian_gray: row stride smaller than a row");
+    bool fast = false;
+    if (const char* e = gf_gauss_launch(src, dst, width, height, src_stride, dst_stride, radius, sigma, stream, &fast))
+        return fail(GF_ERR_CUDA, "gf_gaussian_gray: %s", e);
+    g_launches += 1;
+    g_kernel = fast ? "gauss4" : "gauss";
+    return GF_OK;
 }
 
 const char* gf_last_kernel(void) { return g_kernel; }

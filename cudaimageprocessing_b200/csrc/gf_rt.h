@@ -12,6 +12,7 @@
 #define GF_LAUNCH(kernel, grid, block, smem, stream, ...) GF_EMU_LAUNCH(kernel, grid, block, smem, __VA_ARGS__)
 static inline const char* gf_rt_launch_error() { return nullptr; }
 template <class K> static inline const char* gf_rt_set_smem(K, size_t) { return nullptr; }
+template <class K> static inline int gf_rt_ctas_per_sm(K, int, size_t) { return 4; }
 static inline const char* gf_rt_alloc_async(void** p, size_t n, void*)
 {   // 256-byte aligned like cudaMallocAsync (the tuned kernels check the alignment of every plane)
     *p = std::aligned_alloc(256, (n + 255) / 256 * 256);
@@ -38,6 +39,13 @@ template <class K> static inline const char* gf_rt_set_smem(K kernel, size_t byt
     if (bytes <= 48 * 1024) return nullptr;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+// resident CTAs per SM of a kernel (registers, shared memory, threads): the wave size of the band choosers
+template <class K> static inline int gf_rt_ctas_per_sm(K kernel, int threads, size_t smem)
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
 }
 static inline const char* gf_rt_alloc_async(void** p, size_t n, void* stream)
 {

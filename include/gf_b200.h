@@ -169,6 +169,15 @@ int gf_integral_u8_i64(const unsigned char* src, int64_t* integral, int64_t* scr
 int gf_integral_u8_i32_padded(const unsigned char* src, int32_t* integral, int src_width, int src_height,
                               int64_t src_stride, int dst_width, int dst_height, void* stream);
 
+/* Separable Gaussian blur of a float32 gray image (replaces the reference's
+   GaussianFilter/gaussian.cu kernels gGaussNaive/Const/Share/Split/Optim, :25-306, as driven by
+   gaussianComparasion, :409-660): taps = cv::getGaussianKernel(2*radius+1, sigma, CV_32F)
+   (sigma <= 0: OpenCV's rule), border REFLECT101 (reflectBorder, GaussianFilter/gaussian.h),
+   i.e. the result of cv::GaussianBlur(src, dst, Size(2r+1, 2r+1), sigma, sigma) to float32
+   rounding.  DEVICE pointers, strides in elements (0 = width), radius 0..64, src != dst. */
+int gf_gaussian_gray(const float* src, float* dst, int width, int height, int64_t src_stride, int64_t dst_stride,
+                     int radius, double sigma, void* stream);
+
 /* Which kernel family the last gf_guided_* call on this thread used ("fast_r8", "generic"...)
    and how many kernels it launched; for tests and bench.py's gpu_launches. */
 const char* gf_last_kernel(void);

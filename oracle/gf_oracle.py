@@ -252,3 +252,45 @@ def guided_filter_gray_u8(I_u8, p_u8, r, eps, border=BORDER_REFLECT101):
     """The reference demo's whole pipeline on 8-bit planes: convertTo float, the float32 CPU composition
     (main.cpp:236-252), convertTo(CV_8U, 255) (main.cpp:295-297)."""
     return to_u8(guided_filter_gray(u8_to_f32(I_u8), u8_to_f32(p_u8), r, eps, border, np.float32))
+
+
+# ---- GaussianFilter/ module (SURVEY 8(f) rank 3) -----------------------------------------------------
+_SMALL_GAUSS = {1: [1.0], 3: [0.25, 0.5, 0.25], 5: [0.0625, 0.25, 0.375, 0.25, 0.0625],
+                7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125]}
+
+
+def gaussian_kernel_1d(radius: int, sigma: float) -> np.ndarray:
+    """cv::getGaussianKernel(2r+1, sigma, CV_32F) restated -- the taps GaussianFilter/gaussian.cu:437 builds
+    for every kernel it launches (and cv::GaussianBlur uses for the host result it compares with, :441).
+    Returned as float32 (the values the filters multiply with)."""
+    n = 2 * radius + 1
+    if sigma <= 0 and n in _SMALL_GAUSS:
+        return np.asarray(_SMALL_GAUSS[n], np.float32)
+    if sigma <= 0:
+        sigma = 0.3 * ((n - 1) * 0.5 - 1.0) + 0.8
+    x = np.arange(n, dtype=np.float64) - radius
+    t = np.exp(-0.5 / (sigma * sigma) * x * x)        # OpenCV >= 4.x: all in double, one rounding to float at the end
+    return (t * (1.0 / t.sum())).astype(np.float32)
+
+
+def gaussian_blur_gray(img: np.ndarray, radius: int, sigma: float) -> np.ndarray:
+    """Separable Gaussian blur with REFLECT101 borders (reflectBorder, GaussianFilter/gaussian.h; the
+    separable form is gGaussSplit / gGaussOptim, gaussian.cu:129-306), float64 accumulation of the
+    float32 taps: the value cv::GaussianBlur and every reference kernel approximate in float32."""
+    k = gaussian_kernel_1d(radius, sigma).astype(np.float64)
+    a = np.asarray(img, np.float64)
+    h, w = a.shape
+
+    def refl(i, n):
+        if n == 1:
+            return np.zeros_like(i)
+        i = np.abs(i)
+        period = 2 * n - 2
+        i = i % period
+        return np.where(i >= n, period - i, i)
+    xs = refl(np.arange(-radius, w + radius), w)
+    ys = refl(np.arange(-radius, h + radius), h)
+    ap = a[:, xs]
+    hor = sum(k[j] * ap[:, j:j + w] for j in range(2 * radius + 1))
+    hp = hor[ys, :]
+    return sum(k[j] * hp[j:j + h, :] for j in range(2 * radius + 1))
