@@ -42,6 +42,35 @@ dist.barrier(); torch.cuda.synchronize()
 D.exchange_halos_inplace([bufI, bufP], H, rank, world, r)
 torch.cuda.synchronize()
 res["kernel_hash_after_exchange_ms"] = t_kernel()
+
+
+def loop(sync_between, n=5):
+    ex0, ex1, k1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    t_ex = t_k = 0.0
+    for _ in range(n):
+        dist.barrier(); torch.cuda.synchronize()
+        ex0.record(stream)
+        D.exchange_halos_inplace([bufI, bufP], H, rank, world, r)
+        ex1.record(stream)
+        if sync_between:
+            torch.cuda.synchronize()
+            ex1.record(stream)
+        D.filter_strip(api, bufI, bufP, qs, H, rank, world, r, 1e-2, 0, sp)
+        k1.record(stream)
+        torch.cuda.synchronize()
+        t_k += ex1.elapsed_time(k1)
+    return round(t_k / n, 3)
+
+
+res["loop_kernel_ms"] = loop(False)
+res["loop_kernel_sync_between_ms"] = loop(True)
+res["loop_kernel_again_ms"] = loop(False)
+# the allocation pattern of scaling.py: a large batch allocated and released before the strip buffers exist
+big = torch.rand((64, 1080, 1920, 3), device="cuda"); big2 = torch.rand((64, 1080, 1920), device="cuda")
+del big, big2
+torch.cuda.empty_cache()
+res["loop_kernel_after_alloc_free_ms"] = loop(False)
+res["kernel_alone_end_ms"] = t_kernel()
 res["nan_in_bufs"] = int(torch.isnan(bufI).sum() + torch.isnan(bufP).sum())
 res["absmax"] = float(max(bufI.abs().max(), bufP.abs().max()))
 res["kernel"] = api.last_kernel()
