@@ -70,7 +70,7 @@ def _cuda():
 
 
 def _pads(img, fast):
-    """fast: row strides that are multiples of 4 floats (the 4-columns-per-thread kernel, radii 1..8);
+    """fast: row strides that are multiples of 4 floats (the 4-columns-per-thread kernel, radii 1..16);
     otherwise odd strides (the thread-per-column kernel)"""
     w = img.shape[1]
     return ((-w) % 4 + 4, (-w) % 4 + 8) if fast else ((-w) % 2 + 3, (-w) % 2 + 5)
@@ -82,14 +82,14 @@ def test_gaussian_emulated_golden(fast):
     for img, r, s, blur, _ in _golden():
         spad, dpad = _pads(img, fast)
         q = _run(api, up, down, img, r, s, spad=spad, dpad=dpad)
-        assert api.last_kernel() == ("gauss4" if fast and 1 <= r <= 8 else "gauss")
+        assert api.last_kernel() == ("gauss4" if fast and 1 <= r <= 16 else "gauss")
         assert np.abs(q - blur).max() <= TOL, (r, s)
         assert np.abs(q - O.gaussian_blur_gray(img, r, s)).max() <= TOL, (r, s)
 
 
 @pytest.mark.parametrize("shape,r,sigma", [((1, 1), 0, 1.0), ((3, 5), 4, 2.0), ((40, 700), 8, 3.0), ((150, 260), 2, 0.8),
                                            ((30, 64), 20, 6.0), ((200, 33), 64, 20.0), ((90, 1100), 8, 2.0), ((70, 1003), 5, 1.2),
-                                           ((300, 40), 7, 2.0), ((2, 3), 8, 3.0), ((60, 520), 1, 0.5)])
+                                           ((300, 40), 7, 2.0), ((2, 3), 8, 3.0), ((60, 520), 1, 0.5), ((80, 600), 13, 4.0), ((50, 1100), 16, 6.0)])
 def test_gaussian_emulated_shapes(shape, r, sigma):
     """1x1, images narrower than the radius (repeated reflection), several strips and bands, the largest
     radius, widths that are not a multiple of 4 (partial last vector), both kernels where both apply"""
@@ -99,7 +99,7 @@ def test_gaussian_emulated_shapes(shape, r, sigma):
     for fast in (True, False):
         spad, dpad = _pads(img, fast)
         q = _run(api, up, down, img, r, sigma, spad=spad, dpad=dpad)
-        assert api.last_kernel() == ("gauss4" if fast and 1 <= r <= 8 else "gauss")
+        assert api.last_kernel() == ("gauss4" if fast and 1 <= r <= 16 else "gauss")
         assert np.abs(q - ref).max() <= TOL
 
 
@@ -120,7 +120,7 @@ def test_gaussian_gpu_golden():
         for img, r, s, blur, _ in _golden():
             spad, dpad = _pads(img, fast)
             q = _run(api, up, down, img, r, s, spad=spad, dpad=dpad)
-            assert api.last_kernel() == ("gauss4" if fast and 1 <= r <= 8 else "gauss")
+            assert api.last_kernel() == ("gauss4" if fast and 1 <= r <= 16 else "gauss")
             assert np.abs(q - blur).max() <= TOL, (r, s)
 
 
@@ -136,7 +136,7 @@ def test_gaussian_gpu_parity(shape, r, sigma):
     for fast in (True, False):
         spad, dpad = _pads(img, fast)
         q = _run(api, up, down, img, r, sigma, spad=spad, dpad=dpad)
-        assert api.last_kernel() == ("gauss4" if fast and 1 <= r <= 8 else "gauss")
+        assert api.last_kernel() == ("gauss4" if fast and 1 <= r <= 16 else "gauss")
         assert np.abs(q - ref).max() <= TOL
     c = _run(api, up, down, np.full(shape, 0.625, np.float32), r, sigma, spad=_pads(img, True)[0], dpad=_pads(img, True)[1])
     assert np.abs(c - 0.625).max() <= 1e-6
