@@ -440,3 +440,35 @@ def test_against_reference_gpu_code(be):
     e_ref, e_ours = np.abs(dq.cpu().numpy() - o64).max(), np.abs(oursA - o64).max()
     print(f"path A r=8 4K: |ref_gpu - f64| = {e_ref:.3e} (float32 integral image), |ours - f64| = {e_ours:.3e}")
     assert e_ours <= TOL
+
+
+@pytest.mark.gpu
+def test_demo_driver_cures_png(tmp_path, capsys):
+    """the cuda_guided_filter-compatible driver (cudaimageprocessing_b200/demo.py = the reference's
+    cudaSmallGuidedDemo, main.cpp:178-312): same arguments, 8-bit gray inputs -> /255 -> 3840x2160 -> filter -> `_cures.png`.
+    The PNG must equal the oracle's result on the same pre-processed planes to 1 LSB on at most 0.01 % of the pixels
+    (the 8x upscaled planes put many results on x.5 ties; same bar as tests/test_u8_io.py)."""
+    cv2 = pytest.importorskip("cv2")
+    from cudaimageprocessing_b200 import demo
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:270, 0:480]
+    base = 128 + 90 * np.sin(xx / 37.0) * np.cos(yy / 23.0)
+    src8 = np.clip(base + rng.normal(0, 12, base.shape), 0, 255).astype(np.uint8)
+    gd8 = np.clip(base, 0, 255).astype(np.uint8)
+    sp, gp = str(tmp_path / "in.png"), str(tmp_path / "guide.png")
+    cv2.imwrite(sp, src8); cv2.imwrite(gp, gd8)
+    assert demo.main(["7", "0.3", "3", sp, gp]) == 0
+    text = capsys.readouterr().out
+    assert "Time cost of CUDA guided filter:" in text and "kernel:" in text
+    got = cv2.imread(str(tmp_path / "in_cures.png"), cv2.IMREAD_GRAYSCALE)
+    assert got is not None and got.shape == (2160, 3840)
+    src = cv2.resize(src8.astype(np.float32) * np.float32(1.0 / 255.0), (3840, 2160))
+    gd = cv2.resize(gd8.astype(np.float32) * np.float32(1.0 / 255.0), (3840, 2160))
+    want = O.to_u8(O.guided_filter_gray(gd, src, 7, 0.3, 0))
+    d = got.astype(int) - want.astype(int)
+    assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= d.size // 10000
+    # a missing guide falls back to the 3x3 median of the source (main.cpp:199-203); a missing source is reported, not raised
+    assert demo.main(["2", "0.1", "1", sp, str(tmp_path / "nope.png")]) == 0
+    assert "Guided image is missing" in capsys.readouterr().out
+    assert demo.main(["2", "0.1", "1", str(tmp_path / "nope.png")]) == 0
+    assert "Can not read source image" in capsys.readouterr().out
