@@ -61,6 +61,7 @@ def main():
     ap.add_argument("--giga", type=int, default=32768)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--r", type=int, default=16)
+    ap.add_argument("--skip3", action="store_true", help="skip the config-3 leg (diagnostics)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
@@ -78,6 +79,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- config 3: batch of 1080p colour-guide frames, sharded by frame ----------------
+    if args.skip3:
+        args.frames = world          # one frame per rank: the leg becomes negligible
     f0, f1 = D.shard_frames(args.frames, rank, world)
     n = f1 - f0
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
