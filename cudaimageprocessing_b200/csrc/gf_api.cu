@@ -21,6 +21,7 @@
 #include "gf_fast.cuh"
 #include "gf_wp.cuh"
 #include "gf_s8.cuh"
+#include "gf_ws.cuh"
 #include "gf_c4.cuh"
 #endif
 
@@ -178,6 +179,7 @@ int run_job(const Job& j)
     {
         const char* name = nullptr;
         const char* e = gf_c4_try(j, &done, &name);
+        if (!done) e = gf_ws_try(j, &done, &name);
         if (!done) e = gf_s8_try(j, &done, &name);
         if (!done) e = gf_wp_try(j, &done, &name);
         if (!done) e = gf_fast_try(j, &done, &name);
@@ -276,7 +278,11 @@ static bool run_planar(const gf_filter& h, const float* guide, const float* src,
     if (h.gch > 1) shuffle(true, guide, gs, gp, C);
     bool done = false;
     const char* name = nullptr;
-    const char* e = check_common(j) == GF_OK ? gf_s8_try(j, &done, &name) : nullptr;
+    const char* e = nullptr;
+    if (check_common(j) == GF_OK) {
+        e = gf_ws_try(j, &done, &name);
+        if (!done) e = gf_s8_try(j, &done, &name);
+    }
     if (!done) {                                   // not a job for the tuned kernel: nothing was written to dst
         gf_rt_free_async(scratch, stream);
         return false;

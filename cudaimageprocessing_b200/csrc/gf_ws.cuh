@@ -1,0 +1,668 @@
+// gf_ws.cuh -- round-2 headline kernel: WARP-SPECIALISED fused guided filter (gray, float32).
+//
+// Why (profiles/r1_s8_full_summary.txt): gf_s8 issues 28 M warp-instructions per 4K frame
+// (485 per 224 output px), a third of them in band ramps, at 255 registers and 1.7 warps per scheduler.
+// This kernel is built around the instruction count instead:
+//   * a lane owns K ADJACENT columns (K = 8, 12 or 16): the cross-lane traffic of a (2R+1)-window sum is
+//     2R/K shuffles per pixel and quantity (K = 12, R = 8: 1.33 instead of 2), the strip halo shrinks from
+//     12.5 % to 8.3 % of the loaded columns, and there are fewer, taller strips;
+//   * the window sums run on QUANTITY pairs -- (S_I, S_p), (S_Ip, S_II), (a, b) -- as packed f32x2
+//     prefix/suffix chains: 2(K-1) + ~1.3 K FADD2 per pair and K pixels (the 114 scalar FADDs of gf_s8's
+//     trees are gone), 4 independent chains per producer warp = exactly the FADD2 pipe's latency;
+//   * the two stages are split over WARPS (one CTA per SM, NS streams, 2 NS warps): the producer warp of a
+//     stream owns the four stage-1 column sums (vertical running sums, window sums, a/b solve) and writes
+//     raw (a, b N) rows into a shared-memory ring; the consumer warp owns stage 2 VERTICAL-FIRST (running
+//     column sums of a, b from the ring, ONE window pair per OUTPUT row, q = mean_a I + mean_b, store).
+//     Each scheduler hosts one producer and one consumer, so one warp's shuffle/LDS bursts overlap the
+//     other's arithmetic, and neither carries the other's registers;
+//   * the NS streams of a CTA walk adjacent sub-bands of ONE strip in ALTERNATING directions and share
+//     their a/b rows across the sub-band boundaries through the rings (a stream's first R rows pre-populate
+//     its partner's window, its last R rows complete its other neighbour's), so a band pays the 4R-row ramp
+//     once per CTA (at its two outer ends) instead of once per warp: only the 2R cheap vertical warm-up
+//     rows (loads + adds) remain per stream.
+// Hand-off: monotonic row counters in shared memory (st.release / ld.acquire at CTA scope, nanosleep
+// back-off); the ring has 2R+2 rows, a producer waits only when its consumer is a full row behind.
+// Numerics: additions only inside a window (prefix + suffix, no subtraction of prefixes); the vertical
+// sums slide (add the entering row, subtract the leaving one) over at most GF_WS_MAX_SUB rows per stream
+// before the band is cut (random-walk drift ~1e-7 per 100 rows on [0,1] data; measured in the tests).
+// Borders: the vertical rule is a row map (TRUNCATE: zero rows + counts); horizontally, lanes that lie
+// (partly) outside the image gather their columns through a per-lane column map (the first and last
+// strip only), so mirrored inputs give mirrored a, b and nothing else changes.
+#pragma once
+#include "gf_s8.cuh"
+
+#ifndef GF_WS_NEWTON
+#define GF_WS_NEWTON 1       // one Newton step after MUFU.RCP in the a/b solve
+#endif
+#ifndef GF_WS_NORM2
+#define GF_WS_NORM2 1        // two-term reciprocal of the pixel count (see GfNorm)
+#endif
+
+struct GfWsArgs {
+    const float* guide; const float* src; float* dst; float* A; float* B;
+    int64_t gs, ss, ds, abs_;        // row strides (floats)
+    int64_t gfs, sfs, dfs, abfs;     // frame strides
+    int width, height, buf_y0, buf_rows, out_y0, out_rows, border;
+    int nstrips, nbands, hb, count;
+    float eps;
+};
+
+template <int R, int K, int NS>
+struct GfWsGeom {
+    static_assert(K % 4 == 0 && K >= 4 && K <= 16, "K columns per lane: 4, 8, 12 or 16");
+    static_assert(2 * R + 1 > K, "window must be wider than a lane");
+    static constexpr int KW = 2 * R + 1;
+    static constexpr int HALO = (2 * R + 3) / 4 * 4;     // columns of halo per side (both stages), 16-byte granular
+    static constexpr int WIN = 32 * K;                   // columns a stream loads
+    static constexpr int WOUT = WIN - 2 * HALO;          // columns it writes
+    static constexpr int RING = 2 * R + 2;               // a/b rows per stream
+    static constexpr int ROW_F4 = (K / 2) * 32;          // float4 per ring row: [pair of columns][lane] = (a0, b0, a1, b1)
+    static constexpr size_t ring_bytes = (size_t)RING * ROW_F4 * 16;
+    static constexpr size_t smem_bytes = (size_t)NS * ring_bytes + 128;   // + the 2 NS row counters
+    static constexpr int MIN_SUB = R + 1;                // shortest sub-band whose neighbours can share rows with it
+};
+
+// ---- hand-off primitives --------------------------------------------------------------------------
+#ifdef GF_CPU_EMU
+static inline int gf_ws_ld_acq(const volatile int* p) { return *p; }
+static inline void gf_ws_st_rel(volatile int* p, int v) { *p = v; }
+static inline void gf_ws_pause() { emu::yield_to_scheduler(emu::RUNNABLE); }
+#else
+__device__ __forceinline__ int gf_ws_ld_acq(const volatile int* p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(const_cast<const int*>(p))) : "memory");
+    return v;
+}
+__device__ __forceinline__ void gf_ws_st_rel(volatile int* p, int v)
+{
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(const_cast<int*>(p))), "r"(v) : "memory");
+}
+__device__ __forceinline__ void gf_ws_pause() { __nanosleep(32); }
+#endif
+__device__ __forceinline__ void gf_ws_wait(const volatile int* ctr, int need)
+{
+    while (gf_ws_ld_acq(ctr) < need) gf_ws_pause();
+}
+__device__ __forceinline__ void gf_ws_publish(volatile int* ctr, int val, int lane)
+{
+    __syncwarp();                       // every lane's ring accesses are ordered before lane 0's release
+    if (lane == 0) gf_ws_st_rel(ctr, val);
+}
+
+// ---- (2R+1)-window sums of K adjacent columns per lane, on packed quantity pairs --------------------
+// Column j of lane l covers [j-R, j+R] in lane-local coordinates: the part left of column 0 is a SUFFIX of
+// lane l-dl (plus the totals of the lanes in between when R > K), the part right of column K-1 a PREFIX of
+// lane l+dr, the rest a local prefix / suffix / total.  Additions only.  Complete for every column at least
+// R away from the warp's first and last column.
+__device__ __forceinline__ float2 gf_ws_shfl_up(float2 v, int d)
+{
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ float2 gf_ws_shfl_down(float2 v, int d)
+{
+    return make_float2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
+__host__ __device__ constexpr int gf_ws_fdiv(int a, int k) { return a >= 0 ? a / k : -((-a + k - 1) / k); }
+
+template <int K, int R>
+__device__ __forceinline__ void gf_ws_window(const float2 (&v)[K], float2 (&w)[K])
+{
+    float2 P[K], S[K];
+    P[0] = v[0];
+#pragma unroll
+    for (int j = 1; j < K; ++j) P[j] = gf_add2(P[j - 1], v[j]);
+    S[K - 1] = v[K - 1];
+#pragma unroll
+    for (int j = K - 2; j >= 0; --j) S[j] = gf_add2(S[j + 1], v[j]);
+    constexpr int CM = (R + K - 1) / K;      // farthest lane a window reaches
+    // cumulative totals of the c nearest lanes on either side (only when R > K)
+    float2 TL[CM + 1], TR[CM + 1];
+    TL[0] = TR[0] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 1; c < CM; ++c) {
+        TL[c] = gf_add2(TL[c - 1], gf_ws_shfl_up(P[K - 1], c));
+        TR[c] = gf_add2(TR[c - 1], gf_ws_shfl_down(P[K - 1], c));
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int a = j - R, b = j + R;
+        const int dl = gf_ws_fdiv(a, K), al = a - dl * K;
+        const int dr = gf_ws_fdiv(b, K), bl = b - dr * K;
+        float2 acc = (dl < 0 && dr > 0) ? P[K - 1] : (dl < 0 ? P[b < K ? b : K - 1] : S[a > 0 ? a : 0]);
+        if (dl < 0) {
+            acc = gf_add2(acc, gf_ws_shfl_up(S[al], -dl));
+            if (-dl - 1 > 0) acc = gf_add2(acc, TL[-dl - 1]);
+        }
+        if (dr > 0) {
+            acc = gf_add2(acc, gf_ws_shfl_down(P[bl], dr));
+            if (dr - 1 > 0) acc = gf_add2(acc, TR[dr - 1]);
+        }
+        w[j] = acc;
+    }
+}
+
+// ---- sub-band plan of one CTA ----------------------------------------------------------------------
+// Stream k of n walks output rows ys, ys+d, .. (L of them).  Streams alternate direction (even: up, odd:
+// down), so the boundary between streams 2p and 2p+1 is where both START and the boundary between 2p+1 and
+// 2p+2 is where both END.  At a shared start the partner's first R a/b rows stand in for this stream's
+// rows -1 .. -R; at a shared end the neighbour's last R rows for rows L .. L+R-1.  An outer boundary (the
+// CTA's own band edge) is computed by the stream itself (R extra a/b rows).
+struct GfWsStream {
+    int ys, d, L;
+    int m0, m1;        // own a/b rows [m0, m1) in stream coordinates (row m = image row ys + d m)
+    int sp, ep;        // stream sharing the start / end boundary, -1 = outer
+};
+template <int NS>
+struct GfWsPlan {
+    int n;
+    GfWsStream s[NS];
+};
+
+template <int R, int NS>
+__host__ __device__ inline void gf_ws_plan(int y0, int y1, GfWsPlan<NS>& pl)
+{
+    const int H = y1 - y0;
+    // balance: an outer boundary costs its stream ~R more full rows, so the first and the last stream get
+    // `pen` rows fewer; every stream of a shared plan needs at least R+1 rows
+    const int pen = (R * 7) / 8;
+    int Ls[NS];
+    int n = NS;
+    for (; n > 1; --n) {
+        const int base = (H + 2 * pen) / n, rem = H + 2 * pen - base * n;     // rem in [0, n): one extra row for the first rem streams
+        bool ok = true;
+        for (int k = 0; k < n; ++k) {
+            Ls[k] = base + (k < rem ? 1 : 0) - ((k == 0) + (k == n - 1)) * pen;
+            ok = ok && Ls[k] >= R + 1;
+        }
+        if (ok) break;
+    }
+    if (n == 1) Ls[0] = H;
+    pl.n = n;
+    int b = y0;
+    for (int k = 0; k < NS; ++k) {
+        GfWsStream& s = pl.s[k];
+        if (k >= n) { s.ys = 0; s.d = 1; s.L = 0; s.m0 = s.m1 = 0; s.sp = s.ep = -1; continue; }
+        const int lo = b, hi = b + Ls[k];
+        b = hi;
+        s.L = Ls[k];
+        if (n == 1) { s.d = 1; s.ys = lo; s.sp = s.ep = -1; }
+        else if ((k & 1) == 0) { s.d = -1; s.ys = hi - 1; s.sp = k + 1 < n ? k + 1 : -1; s.ep = k >= 1 ? k - 1 : -1; }
+        else { s.d = 1; s.ys = lo; s.sp = k - 1; s.ep = k + 1 < n ? k + 1 : -1; }
+        s.m0 = s.sp >= 0 ? 0 : -R;
+        s.m1 = s.ep >= 0 ? s.L : s.L + R;
+    }
+}
+
+// ---- stage 1: producer warp -------------------------------------------------------------------------
+template <int R, int K, int NS, bool TRUNC, bool EDGE>
+__device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<NS>& pl, int k, int lane, int64_t f, int xl,
+                                             int out_lo, int out_hi, float4* rings, volatile int* ctrl)
+{
+    using G = GfWsGeom<R, K, NS>;
+    constexpr int RING = G::RING, KW = G::KW;
+    const GfWsStream st = pl.s[k];
+    float4* ring = rings + (size_t)k * RING * G::ROW_F4 + lane;
+    const int x0 = xl + lane * K;
+    // EDGE = false: every column of the strip's window lies inside the image (no column map in the code at all)
+    const bool vec = !EDGE || (x0 >= 0 && x0 + K <= a.width);
+    int sx[EDGE ? K : 1];
+    if (EDGE) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) sx[j] = gf_map(x0 + j, a.width, a.border);
+    }
+    const float* gI = a.guide + f * a.gfs;            // column 0 (the column map of EDGE lanes is absolute)
+    const float* gP = a.src + f * a.sfs;
+    const float* gIx = gI + x0;                        // this lane's first column
+    const float* gPx = gP + x0;
+    const int rows_hi = (a.buf_y0 + a.buf_rows < a.height ? a.buf_y0 + a.buf_rows : a.height) - 1 - a.buf_y0;
+
+    // buffer row of stream-local input row t, -1 = a row of zeros (TRUNCATE outside the image)
+    auto row_of = [&](int t) -> int {
+        int y = st.ys + st.d * t;
+        if (TRUNC) { if (y < 0 || y >= a.height) return -1; }
+        else y = gf_s8_map_y(y, a.height, a.border);
+        int rr = y - a.buf_y0;
+        rr = rr < 0 ? 0 : (rr > rows_hi ? rows_hi : rr);
+        return rr;
+    };
+    auto ld_row = [&](const float* plane, const float* planex, int64_t stride, int rr, float (&v)[K]) {
+        if (TRUNC && rr < 0) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) v[j] = 0.f;
+            return;
+        }
+        const int64_t ro = (int64_t)rr * stride;
+        if (vec) {
+            const float* rp = planex + ro;
+#pragma unroll
+            for (int c = 0; c < K / 4; ++c) {
+                const float4 t = *reinterpret_cast<const float4*>(rp + 4 * c);
+                v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+            }
+        } else if (EDGE) {
+            const float* rp = plane + ro;
+#pragma unroll
+            for (int j = 0; j < K; ++j) v[j] = sx[j] >= 0 ? rp[sx[j]] : 0.f;
+        }
+    };
+
+    // X = (sum I, sum p), Y = (sum I p, sum I I) over the current 2R+1 rows, per column
+    float2 X[K], Y[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) X[j] = Y[j] = make_float2(0.f, 0.f);
+
+    // warm-up: input rows [m0-R, m0+R) -- loads and adds only, CH rows in flight
+    {
+        constexpr int CH = K >= 16 ? 2 : 4;
+        const int t_end = st.m0 + R;
+#pragma unroll 1
+        for (int t0 = st.m0 - R; t0 < t_end; t0 += CH) {
+            float bI[CH][K], bP[CH][K];
+#pragma unroll
+            for (int q = 0; q < CH; ++q) {
+                const int rr = row_of(t0 + q < t_end ? t0 + q : t_end - 1);     // (rows past the end: loaded again, not added)
+                ld_row(gI, gIx, a.gs, rr, bI[q]);
+                ld_row(gP, gPx, a.ss, rr, bP[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < CH; ++q) {
+                if (t0 + q >= t_end) break;
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    X[j].x += bI[q][j]; X[j].y += bP[q][j];
+                    Y[j].x = fmaf(bI[q][j], bP[q][j], Y[j].x);
+                    Y[j].y = fmaf(bI[q][j], bI[q][j], Y[j].y);
+                }
+            }
+        }
+    }
+
+    float nI[K], nP[K], oI[K], oP[K];
+    {
+        const int rr = row_of(st.m0 + R);
+        ld_row(gI, gIx, a.gs, rr, nI);
+        ld_row(gP, gPx, a.ss, rr, nP);
+#pragma unroll
+        for (int j = 0; j < K; ++j) oI[j] = oP[j] = 0.f;
+    }
+    float cx[K];                     // TRUNCATE: in-image columns of the window of each column
+    if (TRUNC) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) cx[j] = gf_count(x0 + j, a.width, R, GF_TRUNCATE);
+    }
+    const float Nf = (float)(KW * KW);
+    const float epsNN = a.eps * Nf * Nf;
+    const GfNorm nk = gf_norm_make(Nf);
+    volatile int* prod = ctrl + 2 * k;
+    const volatile int* cons_own = ctrl + 2 * k + 1;
+    const volatile int* cons_sp = ctrl + 2 * (st.sp >= 0 ? st.sp : k) + 1;
+    const int n_last = st.L - 1 + R;
+    const int n_last_sp = st.sp >= 0 ? pl.s[st.sp].L - 1 + R : 0;
+    int slot = 0;
+
+#pragma unroll 1
+    for (int m = st.m0; m < st.m1; ++m) {
+        // ---- vertical: row m+R enters, row m-R-1 leaves ----
+#pragma unroll
+        for (int c = 0; c < K / 2; ++c) {      // (entering - leaving) on the column pairs the loads deliver: FADD2
+            const float2 dI = gf_sub2(make_float2(nI[2 * c], nI[2 * c + 1]), make_float2(oI[2 * c], oI[2 * c + 1]));
+            const float2 dP = gf_sub2(make_float2(nP[2 * c], nP[2 * c + 1]), make_float2(oP[2 * c], oP[2 * c + 1]));
+            X[2 * c].x += dI.x; X[2 * c + 1].x += dI.y;
+            X[2 * c].y += dP.x; X[2 * c + 1].y += dP.y;
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            Y[j].x = fmaf(-oI[j], oP[j], fmaf(nI[j], nP[j], Y[j].x));
+            Y[j].y = fmaf(-oI[j], oI[j], fmaf(nI[j], nI[j], Y[j].y));
+        }
+        // ---- rows of the next iteration (a whole iteration to land) ----
+        if (m + 1 < st.m1) {
+            const int rn = row_of(m + 1 + R), ro = row_of(m - R);
+            ld_row(gI, gIx, a.gs, rn, nI);
+            ld_row(gP, gPx, a.ss, rn, nP);
+            ld_row(gI, gIx, a.gs, ro, oI);
+            ld_row(gP, gPx, a.ss, ro, oP);
+        }
+        // ---- horizontal: window sums of the two quantity pairs ----
+        float2 hX[K], hY[K];
+        gf_ws_window<K, R>(X, hX);
+        gf_ws_window<K, R>(Y, hY);
+        // ---- a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2),  bN = S_p - a S_I  (b = bN / N) ----
+        float av[K], bv[K];
+        if (TRUNC) {
+            const int yc = st.ys + st.d * m;
+            const bool rowin = yc >= 0 && yc < a.height;
+            const float cy = gf_s8_cnt_y<R>(yc, a.height);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float n2 = cx[j] * cy;
+                const float num = fmaf(n2, hY[j].x, -(hX[j].x * hX[j].y));
+                const float den = fmaf(-hX[j].x, hX[j].x, fmaf(n2, hY[j].y, a.eps * n2 * n2));
+                float rc = gf_s8_rcp(den);
+                rc = fmaf(fmaf(-den, rc, 1.0f), rc, rc);
+                float rn = gf_s8_rcp(n2);
+                rn = fmaf(fmaf(-n2, rn, 1.0f), rn, rn);
+                const float aa = num * rc;
+                const float bb = fmaf(-aa, hX[j].x, hX[j].y) * rn;
+                const bool ok = rowin && (!EDGE || sx[j] >= 0);
+                av[j] = ok ? aa : 0.f;
+                bv[j] = ok ? bb : 0.f;
+            }
+        } else {
+            // (num, den) = N (S_Ip, S_II) + (0, eps N^2) - S_I (S_p, S_I): two FFMA2 (the broadcast and the
+            // swapped operand are operand modifiers of the packed instructions on sm_100)
+            const float2 cN = make_float2(Nf, Nf), cE = make_float2(0.f, epsNN);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float2 t = gf_fma2(cN, hY[j], cE);
+                const float2 u = gf_fma2(make_float2(-hX[j].x, -hX[j].x), make_float2(hX[j].y, hX[j].x), t);
+                float rc = gf_s8_rcp(u.y);
+                if (GF_WS_NEWTON) rc = fmaf(fmaf(-u.y, rc, 1.0f), rc, rc);
+                av[j] = u.x * rc;
+                bv[j] = fmaf(-av[j], hX[j].x, hX[j].y);
+            }
+        }
+        // ---- the ring slot of row m held row m-RING: every consumer of that row must be done with it ----
+        const int idx = m - st.m0;
+        if (idx >= RING) {
+            const int mm = m - RING;
+            const int use = mm + KW < n_last ? mm + KW : n_last;          // last step of the own consumer that reads row mm
+            gf_ws_wait(cons_own, use + R + 1);
+            if (st.sp >= 0 && mm < R) {                                    // ... and of the start partner (its row -1-mm)
+                const int usep = 2 * R - mm < n_last_sp ? 2 * R - mm : n_last_sp;
+                gf_ws_wait(cons_sp, usep + R + 1);
+            }
+        }
+        {
+            float4* rp = ring + slot * G::ROW_F4;
+#pragma unroll
+            for (int c = 0; c < K / 2; ++c) rp[c * 32] = make_float4(av[2 * c], bv[2 * c], av[2 * c + 1], bv[2 * c + 1]);
+        }
+        gf_ws_publish(prod, idx + 1, lane);
+        slot = slot + 1 == RING ? 0 : slot + 1;
+        // ---- optional A / B planes (hGuidedFilter's d_A, d_B): own territory rows, output columns ----
+        if (a.A != nullptr && m >= 0 && m < st.L) {
+            const int y = st.ys + st.d * m;
+            float* pa = a.A + f * a.abfs + (int64_t)(y - a.out_y0) * a.abs_ + x0;
+            float* pb = a.B + f * a.abfs + (int64_t)(y - a.out_y0) * a.abs_ + x0;
+#pragma unroll
+            for (int c = 0; c < K / 4; ++c) {
+                const int xc = x0 + 4 * c;
+                if (xc >= out_lo && xc + 4 <= out_hi) {
+                    float b4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) b4[i] = TRUNC ? bv[4 * c + i] : gf_norm_apply(bv[4 * c + i], nk);
+                    *reinterpret_cast<float4*>(pa + 4 * c) = make_float4(av[4 * c], av[4 * c + 1], av[4 * c + 2], av[4 * c + 3]);
+                    *reinterpret_cast<float4*>(pb + 4 * c) = make_float4(b4[0], b4[1], b4[2], b4[3]);
+                }
+            }
+        }
+    }
+}
+
+// ---- stage 2: consumer warp -------------------------------------------------------------------------
+template <int R, int K, int NS, bool TRUNC>
+__device__ __forceinline__ void gf_ws_stage2(const GfWsArgs& a, const GfWsPlan<NS>& pl, int k, int lane, int64_t f, int xl,
+                                             int out_lo, int out_hi, const float4* rings, volatile int* ctrl)
+{
+    using G = GfWsGeom<R, K, NS>;
+    constexpr int RING = G::RING, KW = G::KW;
+    const GfWsStream st = pl.s[k];
+    const int x0 = xl + lane * K;
+    const float* gI = a.guide + f * a.gfs + x0;
+    float* gQ = a.dst + f * a.dfs + x0;
+    unsigned omask = 0;                       // 4-column groups this lane stores
+#pragma unroll
+    for (int c = 0; c < K / 4; ++c) {
+        const int u = lane * K + 4 * c, xc = x0 + 4 * c;
+        if (u >= G::HALO && u + 4 <= G::WIN - G::HALO && xc >= out_lo && xc + 4 <= out_hi) omask |= 1u << c;
+    }
+    float cx[K];
+    if (TRUNC) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) cx[j] = gf_count(x0 + j, a.width, R, GF_TRUNCATE);
+    }
+    // mean_a = sum_a / N, mean_b = sum_bN / N^2, both as two-term reciprocals, on the (a, b) pair at once
+    const GfNorm nk1 = gf_norm_make((float)(KW * KW)), nk2 = gf_norm_make((float)(KW * KW) * (float)(KW * KW));
+    const float2 nh = make_float2(nk1.hi, nk2.hi), nl = make_float2(nk1.lo, nk2.lo);
+    volatile int* cons = ctrl + 2 * k + 1;
+    const int ep_last = st.ep >= 0 ? pl.s[st.ep].L - 1 - pl.s[st.ep].m0 + st.L : 0;    // ring index of row n >= L in the end partner: ep_last - n
+
+    // ring row and producer counter of stream-local a/b row n
+    auto resolve = [&](int n, const float4*& base, const volatile int*& prod, int& idx) {
+        int t = k;
+        idx = n - st.m0;
+        if (n < 0 && st.sp >= 0) { t = st.sp; idx = -1 - n; }              // (a shared start: the partner's m0 is 0)
+        else if (n >= st.L && st.ep >= 0) { t = st.ep; idx = ep_last - n; }
+        base = rings + (t * RING + idx % RING) * G::ROW_F4 + lane;
+        prod = ctrl + 2 * t;
+    };
+    auto ld_guide = [&](int i, float (&g)[K]) {
+        const int y = st.ys + st.d * i;
+        const float* rp = gI + (int64_t)(y - a.buf_y0) * a.gs;
+#pragma unroll
+        for (int c = 0; c < K / 4; ++c) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (omask >> c & 1) t = *reinterpret_cast<const float4*>(rp + 4 * c);
+            g[4 * c] = t.x; g[4 * c + 1] = t.y; g[4 * c + 2] = t.z; g[4 * c + 3] = t.w;
+        }
+    };
+
+    float2 V[K];                              // (sum a, sum bN) over the current 2R+1 rows, per column
+#pragma unroll
+    for (int j = 0; j < K; ++j) V[j] = make_float2(0.f, 0.f);
+    float g[K];
+    ld_guide(0, g);
+    const int n_last = st.L - 1 + R;
+#pragma unroll 1
+    for (int n = -R; n <= n_last; ++n) {
+        const float4* nb; const volatile int* np; int ni;
+        resolve(n, nb, np, ni);
+        gf_ws_wait(np, ni + 1);
+        float4 nw[K / 2];
+#pragma unroll
+        for (int c = 0; c < K / 2; ++c) nw[c] = nb[c * 32];
+        if (n - KW >= -R) {
+            const float4* ob; const volatile int* op; int oi;
+            resolve(n - KW, ob, op, oi);
+#pragma unroll
+            for (int c = 0; c < K / 2; ++c) {
+                const float4 o = ob[c * 32];
+                V[2 * c] = gf_add2(V[2 * c], gf_sub2(make_float2(nw[c].x, nw[c].y), make_float2(o.x, o.y)));
+                V[2 * c + 1] = gf_add2(V[2 * c + 1], gf_sub2(make_float2(nw[c].z, nw[c].w), make_float2(o.z, o.w)));
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < K / 2; ++c) {
+                V[2 * c] = gf_add2(V[2 * c], make_float2(nw[c].x, nw[c].y));
+                V[2 * c + 1] = gf_add2(V[2 * c + 1], make_float2(nw[c].z, nw[c].w));
+            }
+        }
+        gf_ws_publish(cons, n + R + 1, lane);       // the ring rows are in registers: the producer may move on
+        if (n < R) continue;
+        // ---- output row i = n - R ----
+        const int i = n - R;
+        float2 W[K];
+        gf_ws_window<K, R>(V, W);
+        float q[K];
+        if (TRUNC) {
+            const int y = st.ys + st.d * i;
+            const float cy = gf_s8_cnt_y<R>(y, a.height);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float n2 = cx[j] * cy;
+                float rn = gf_s8_rcp(n2);
+                rn = fmaf(fmaf(-n2, rn, 1.0f), rn, rn);
+                q[j] = fmaf(W[j].x, g[j], W[j].y) * rn;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float2 m = GF_WS_NORM2 ? gf_fma2(W[j], nh, gf_mul2(W[j], nl)) : gf_mul2(W[j], nh);
+                q[j] = fmaf(m.x, g[j], m.y);
+            }
+        }
+        {
+            const int y = st.ys + st.d * i;
+            float* qp = gQ + (int64_t)(y - a.out_y0) * a.ds;
+#pragma unroll
+            for (int c = 0; c < K / 4; ++c)
+                if (omask >> c & 1) *reinterpret_cast<float4*>(qp + 4 * c) = make_float4(q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
+        }
+        if (i + 1 < st.L) ld_guide(i + 1, g);
+    }
+}
+
+// ---- kernel: one CTA = one (frame, strip, band); warps [0, NS) produce, [NS, 2 NS) consume ------------
+template <int R, int K, int NS, bool TRUNC>
+__global__ void __launch_bounds__(64 * NS, 1) gf_ws_gray_kernel(const GF_GRID_CONSTANT GfWsArgs a)
+{
+    using G = GfWsGeom<R, K, NS>;
+    GF_DYN_SMEM(float4, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    volatile int* ctrl = reinterpret_cast<volatile int*>(smem + (size_t)NS * G::RING * G::ROW_F4);
+    const long item = (long)blockIdx.x;
+    const long per_frame = (long)a.nstrips * a.nbands;
+    const int64_t f = item / per_frame;
+    const int rem = (int)(item % per_frame);
+    const int band = rem / a.nstrips, strip = rem % a.nstrips;       // strips of one band run side by side (halo hits in L2)
+    const int y0 = a.out_y0 + band * a.hb;
+    const int y1 = y0 + a.hb < a.out_y0 + a.out_rows ? y0 + a.hb : a.out_y0 + a.out_rows;
+    if (threadIdx.x < 2 * NS) ctrl[threadIdx.x] = 0;
+    __syncthreads();
+    GfWsPlan<NS> pl;
+    gf_ws_plan<R, NS>(y0, y1, pl);
+    const int xl = strip * G::WOUT - G::HALO;
+    const int out_lo = strip * G::WOUT;
+    const int out_hi = out_lo + G::WOUT < a.width ? out_lo + G::WOUT : a.width;
+    const int k = warp < NS ? warp : warp - NS;
+    if (k >= pl.n) return;
+    if (warp < NS) {
+        if (xl >= 0 && xl + G::WIN <= a.width) gf_ws_stage1<R, K, NS, TRUNC, false>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);
+        else gf_ws_stage1<R, K, NS, TRUNC, true>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);
+    }
+    else gf_ws_stage2<R, K, NS, TRUNC>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+#ifndef GF_NO_HOST
+// Longest sub-band a stream walks with sliding (add / subtract) vertical sums before the band is cut.
+#ifndef GF_WS_MAX_SUB
+#define GF_WS_MAX_SUB 512
+#endif
+
+struct GfWsTune {          // developer knobs, read ONCE (first launch); nothing here changes results
+    int disable;           // GF_DISABLE_WS=1: hand every job to the older kernels
+    int k;                 // GF_WS_K = 8 / 12 / 16: force a column count (default: per radius)
+    int hb;                // GF_WS_HB: force the band height
+};
+static inline const GfWsTune& gf_ws_tune()
+{
+    static const GfWsTune t = [] {
+        GfWsTune v{0, 0, 0};
+        if (const char* e = getenv("GF_DISABLE_WS")) v.disable = atoi(e);
+        if (const char* e = getenv("GF_WS_K")) v.k = atoi(e);
+        if (const char* e = getenv("GF_WS_HB")) v.hb = atoi(e);
+        return v;
+    }();
+    return t;
+}
+
+// Band height: CTAs run in waves of `sms` (one CTA per SM); a CTA's time ~ its slowest stream:
+//   (hb + 2 x 0.85 R outer rows) / NS  +  2R warm-up rows at ~0.2  +  ~2 rows of start-up.
+template <int R, int NS>
+static inline int gf_ws_pick_band(int rows, long nstrips_x_count, int sms)
+{
+    const int hb_min = NS * (R + 1) + 2 * R;
+    int best_hb = rows;
+    double best = 1e300;
+    for (int nb = 1; nb <= 4096; ++nb) {
+        int hb = (rows + nb - 1) / nb;
+        if (hb < hb_min && nb > 1) break;
+        if (hb > NS * GF_WS_MAX_SUB) continue;
+        const long items = nstrips_x_count * ((rows + hb - 1) / hb);
+        const long waves = (items + sms - 1) / sms;
+        const double cost = (double)waves * ((hb + 1.7 * R) / NS + 0.4 * R + 2.0);
+        if (cost < best * 0.999) { best = cost; best_hb = hb; }
+    }
+    return best_hb;
+}
+
+template <int R, int K, int NS>
+static const char* gf_ws_launch(const Job& j)
+{
+    using G = GfWsGeom<R, K, NS>;
+    static_assert(G::smem_bytes <= 227 * 1024, "rings do not fit");
+    int sms = 148, mj = 0, mn = 0;
+    gf_rt_device_info(&sms, &mj, &mn);
+    GfWsArgs a;
+    a.guide = j.guide.ptr; a.src = j.src.ptr; a.dst = const_cast<float*>(j.dst.ptr);
+    a.A = const_cast<float*>(j.A.ptr); a.B = const_cast<float*>(j.B.ptr);
+    a.gs = j.guide.stride; a.ss = j.src.stride; a.ds = j.dst.stride; a.abs_ = j.A.ptr ? j.A.stride : 0;
+    a.gfs = j.guide.frame_stride; a.sfs = j.src.frame_stride; a.dfs = j.dst.frame_stride; a.abfs = j.A.ptr ? j.A.frame_stride : 0;
+    a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
+    a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
+    a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
+    int hb = gf_ws_pick_band<R, NS>(j.out_rows, (long)a.nstrips * j.count, sms);
+    if (gf_ws_tune().hb > 0) hb = gf_ws_tune().hb;
+    if (hb > j.out_rows) hb = j.out_rows;
+    if (hb < 1) hb = 1;
+    a.hb = hb;
+    a.nbands = (j.out_rows + hb - 1) / hb;
+    const long items = (long)a.nstrips * a.nbands * j.count;
+    dim3 grid((unsigned)items), block(64 * NS);
+    const char* e;
+    if (j.border == GF_TRUNCATE) {
+        auto kf = gf_ws_gray_kernel<R, K, NS, true>;
+        if ((e = gf_rt_set_smem(kf, G::smem_bytes))) return e;
+        GF_LAUNCH(kf, grid, block, G::smem_bytes, j.stream, a);
+    } else {
+        auto kf = gf_ws_gray_kernel<R, K, NS, false>;
+        if ((e = gf_rt_set_smem(kf, G::smem_bytes))) return e;
+        GF_LAUNCH(kf, grid, block, G::smem_bytes, j.stream, a);
+    }
+    return gf_rt_launch_error();
+}
+
+static const char* gf_ws_try(const Job& j, bool* done, const char** name)
+{
+    *done = false;
+    const GfWsTune& tn = gf_ws_tune();
+    if (tn.disable || j.color) return nullptr;
+    if ((j.A.ptr == nullptr) != (j.B.ptr == nullptr)) return nullptr;
+    const Plane* pl[5] = {&j.guide, &j.src, &j.dst, &j.A, &j.B};
+    for (int i = 0; i < 5; ++i) {
+        if (!pl[i]->ptr) continue;
+        if (pl[i]->channels != 1 || pl[i]->coff != 0 || (pl[i]->stride & 3) || (pl[i]->frame_stride & 3) || ((uintptr_t)pl[i]->ptr & 15))
+            return nullptr;
+    }
+    if (j.A.ptr && (j.A.stride != j.B.stride || j.A.frame_stride != j.B.frame_stride)) return nullptr;
+    if (j.width & 3) return nullptr;
+    // single reflections only (rows), and bands tall enough for at least one stream with its ramp
+    if (j.height < 4 * j.r + 2 || j.out_rows < 1) return nullptr;
+#define GF_WS_CASE(RR, KK, NN, NAME)                                                  \
+    if (j.r == RR && (tn.k == 0 || tn.k == KK) && j.width >= GfWsGeom<RR, KK, NN>::WOUT) { \
+        *done = true; *name = NAME; return gf_ws_launch<RR, KK, NN>(j);              \
+    }
+#ifdef GF_CPU_EMU
+    GF_WS_CASE(8, 12, 4, "ws_r8_k12")
+    GF_WS_CASE(8, 8, 6, "ws_r8_k8")
+    GF_WS_CASE(4, 8, 4, "ws_r4_k8")
+    GF_WS_CASE(16, 12, 2, "ws_r16_k12")
+#else
+    GF_WS_CASE(8, 12, 4, "ws_r8_k12")
+    GF_WS_CASE(8, 8, 6, "ws_r8_k8")
+    GF_WS_CASE(8, 16, 3, "ws_r8_k16")
+    GF_WS_CASE(7, 12, 4, "ws_r7_k12")
+    GF_WS_CASE(7, 8, 6, "ws_r7_k8")
+    GF_WS_CASE(4, 8, 6, "ws_r4_k8")
+    GF_WS_CASE(5, 8, 6, "ws_r5_k8")
+    GF_WS_CASE(6, 8, 6, "ws_r6_k8")
+    GF_WS_CASE(16, 12, 2, "ws_r16_k12")
+    GF_WS_CASE(16, 8, 3, "ws_r16_k8")
+#endif
+#undef GF_WS_CASE
+    return nullptr;
+}
+#endif  // GF_NO_HOST
