@@ -69,7 +69,7 @@ def one(w, h, r, border=0, iters=40):
     return {"w": w, "h": h, "r": r, "border": border, "kernel": api.last_kernel(), "us": round(ms * 1e3, 2),
             "us_best": round(best * 1e3, 2), "gpix_s": round(w * h / ms / 1e6, 1), "gbs_alg": round(12.0 * w * h / ms / 1e6, 1),
             "frac_6535": round(12.0 * w * h / ms / 1e6 / 6535.7, 4), "max_err_f64": err,
-            "env": {k: v for k, v in os.environ.items() if k.startswith("GF_")}}
+            "env": {k: os.path.basename(v) for k, v in os.environ.items() if k.startswith("GF_")}}
 
 
 def main():
@@ -79,13 +79,21 @@ def main():
         print(json.dumps(one(*a)), flush=True)
         return
     cases = [(3840, 2160, 8), (7680, 4320, 8), (1920, 1080, 8)]
-    envs = [{"GF_DISABLE_WS": "1"}, {"GF_WS_K": "12"}, {"GF_WS_K": "8"}, {"GF_WS_K": "16"}]
-    extra = [({}, (3840, 2160, 16)), ({"GF_DISABLE_WS": "1"}, (3840, 2160, 16)), ({"GF_WS_K": "8"}, (3840, 2160, 16)),
-             ({}, (3840, 2160, 7)), ({}, (3840, 2160, 4)), ({"GF_DISABLE_WS": "1"}, (3840, 2160, 4)),
-             ({}, (3840, 2160, 8, 1)), ({}, (3840, 2160, 8, 2)), ({}, (16384, 8192, 8))]
+    envs = [{"GF_WS": "0"}, {"GF_WS": "1", "GF_WS_K": "12"}, {"GF_WS": "1", "GF_WS_K": "8"}, {"GF_WS": "1", "GF_WS_K": "16"}]
+    extra = [({"GF_WS": "1"}, (3840, 2160, 16)), ({"GF_WS": "0"}, (3840, 2160, 16)), ({"GF_WS": "1", "GF_WS_K": "8"}, (3840, 2160, 16)),
+             ({"GF_WS": "1"}, (3840, 2160, 7)), ({"GF_WS": "1"}, (3840, 2160, 4)), ({"GF_WS": "0"}, (3840, 2160, 4)),
+             ({"GF_WS": "1"}, (3840, 2160, 8, 1)), ({"GF_WS": "1"}, (3840, 2160, 8, 2)), ({"GF_WS": "1"}, (16384, 8192, 8))]
     jobs = [(e, c) for c in cases for e in envs] + extra
     if len(sys.argv) > 1 and sys.argv[1] == "--hb":
-        jobs = [({"GF_WS_K": k, "GF_WS_HB": str(hb)}, (3840, 2160, 8)) for k in ("12", "8") for hb in (60, 84, 110, 167, 240, 360)]
+        jobs = [({"GF_WS": "1", "GF_WS_K": k, "GF_WS_HB": str(hb)}, (3840, 2160, 8)) for k in ("12", "8") for hb in (60, 84, 110, 167, 240, 360)]
+    if len(sys.argv) > 1 and sys.argv[1] == "--variants":      # differently compiled builds: ws_bench.py --variants libA.so libB.so ...
+        libs = sys.argv[2:]
+        jobs = []
+        for lib in libs:
+            path = os.path.join(ROOT, "cudaimageprocessing_b200", lib)
+            for k in ("12", "8"):
+                for c in ((3840, 2160, 8), (7680, 4320, 8)):
+                    jobs.append(({"GF_LIB_PATH": path, "GF_WS": "1", "GF_WS_K": k}, c))
     for env, c in jobs:
         e = dict(os.environ)
         e.update(env)

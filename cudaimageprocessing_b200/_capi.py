@@ -38,6 +38,7 @@ SIGNATURES = {
     "gf_integral_u8_i32_padded": (c_int, [P, P, c_int, c_int, c_int64, c_int, c_int, P]),
     "gf_last_kernel": (ctypes.c_char_p, []),
     "gf_launch_count": (c_int64, []),
+    "gf_set_option": (c_int, [ctypes.c_char_p, c_int]),
 }
 
 
@@ -63,6 +64,10 @@ class GfApi:
 
     def call(self, name: str, *args):
         self._check(getattr(self.cdll, name)(*args))
+
+    def set_option(self, name: str, value: int):
+        """Developer/test knob of the launch paths (include/gf_b200.h: gf_set_option); value < 0 = default."""
+        self.call("gf_set_option", name.encode(), int(value))
 
     def last_kernel(self) -> str:
         return self.cdll.gf_last_kernel().decode()

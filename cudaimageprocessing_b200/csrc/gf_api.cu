@@ -353,6 +353,15 @@ int gf_gaussian_gray(const float* src, float* dst, int width, int height, int64_
 }
 
 const char* gf_last_kernel(void) { return g_kernel; }
+
+int gf_set_option(const char* name, int value)
+{
+    if (!name || std::strncmp(name, "GF_", 3) != 0) return fail(GF_ERR_INVALID, "gf_set_option: option names start with GF_");
+    GfKnobSlot* s = gf_knob_slot(name);
+    if (!s) return fail(GF_ERR_NOMEM, "gf_set_option: option table full");
+    s->value.store(value < 0 ? -1 : value, std::memory_order_relaxed);
+    return GF_OK;
+}
 int64_t gf_launch_count(void) { return g_launches.load(); }
 
 int gf_device_info(int* sm_count, int* cc_major, int* cc_minor)

@@ -352,17 +352,18 @@ static const char* gf_c4_launch(const Job& j)
     constexpr int FIT = (int)((size_t)228 * 1024 / (G::ring_bytes + 1024));
     constexpr int MINB = FIT > 8 ? 8 : (FIT < 1 ? 1 : FIT);
     int warps_sm = MINB;
-    if (const char* e = getenv("GF_C4_WARPS_PER_SM")) warps_sm = atoi(e);
+    warps_sm = GF_KNOB("GF_C4_WARPS_PER_SM", warps_sm);
+    if (warps_sm < 1) warps_sm = 1;
     int hb = gf_pick_band_rows(j.out_rows, R, (long)a.nstrips * j.count, (long)sms * warps_sm, 2 * R + 8);
-    if (const char* e = getenv("GF_C4_HB")) hb = atoi(e);
+    hb = GF_KNOB("GF_C4_HB", hb);
     if (hb < 1) hb = 1;
     if (hb > j.out_rows) hb = j.out_rows;
     a.hb = hb;
     a.nbands = (j.out_rows + hb - 1) / hb;
     long items = (long)a.nstrips * a.nbands * j.count;
     int we = 100;
-    if (const char* e = getenv("GF_C4_EDGE_WEIGHT")) we = atoi(e);
-    if (!getenv("GF_C4_HB"))
+    we = GF_KNOB("GF_C4_EDGE_WEIGHT", we);
+    if (!GF_KNOB_SET("GF_C4_HB"))
         if (const long n = gf_tape_plan(a, R, (long)sms * warps_sm, 2 * R + 8, we)) items = n;
     dim3 grid((unsigned)items), block(32);
     auto k = gf_c4_color_kernel<R, MINB>;
@@ -375,7 +376,7 @@ static const char* gf_c4_try(const Job& j, bool* done, const char** name)
 {
     *done = false;
     if (!j.color || j.border != GF_REFLECT101 || j.A.ptr) return nullptr;
-    if (getenv("GF_DISABLE_C4") || getenv("GF_DISABLE_FAST")) return nullptr;
+    if (GF_KNOB("GF_DISABLE_C4", 0) || GF_KNOB("GF_DISABLE_FAST", 0)) return nullptr;
     if (j.guide.channels != 3 || j.guide.coff != 0 || j.src.channels != 1 || j.src.coff != 0 || j.dst.channels != 1 || j.dst.coff != 0)
         return nullptr;
     const Plane* pl[3] = {&j.guide, &j.src, &j.dst};

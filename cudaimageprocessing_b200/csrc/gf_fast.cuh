@@ -443,12 +443,12 @@ struct GfFastLaunch {
         if (per_sm > by_threads) per_sm = by_threads;
         if (per_sm < 1) per_sm = 1;
         int target = sms * per_sm;
-        if (const char* e = getenv("GF_FAST_CTAS_PER_SM")) target = sms * atoi(e);
+        if (GF_KNOB_SET("GF_FAST_CTAS_PER_SM")) target = sms * GF_KNOB("GF_FAST_CTAS_PER_SM", 1);
         int nb = target / (nstrips * j.count);
         if (nb < 1) nb = 1;
         int hb = (j.out_rows + nb - 1) / nb;
         int hb_min = 6 * R;
-        if (const char* e = getenv("GF_FAST_HB_MIN")) hb_min = atoi(e);
+        hb_min = GF_KNOB("GF_FAST_HB_MIN", hb_min);
         if (hb < hb_min) hb = hb_min;
         if (hb > j.out_rows) hb = j.out_rows;
         a.hb = hb;
@@ -482,7 +482,7 @@ static const char* gf_fast_try(const Job& j, bool* done, const char** name)
 {
     *done = false;
     if (j.color) return nullptr;
-    if (getenv("GF_DISABLE_FAST")) return nullptr;
+    if (GF_KNOB("GF_DISABLE_FAST", 0)) return nullptr;
     const Plane* pl[3] = {&j.guide, &j.src, &j.dst};
     for (int i = 0; i < 3; ++i)
         if (pl[i]->channels != 1 || pl[i]->coff != 0 || (pl[i]->stride & 3) || (pl[i]->frame_stride & 3) ||

@@ -190,7 +190,7 @@ static const char* gf_gauss_launch(const float* src, float* dst, int w, int h, i
     gf_gauss_weights(r, sigma, a.w);
     for (int k = r + 1; k <= GF_GAUSS_MAX_R; ++k) a.w[k] = 0.f;
     const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0 && (ss & 3) == 0 && (ds & 3) == 0;
-    if (r >= 1 && r <= 16 && aligned && !getenv("GF_GAUSS_GENERIC")) {
+    if (r >= 1 && r <= 16 && aligned && !GF_KNOB("GF_GAUSS_GENERIC", 0)) {
         const int HR4 = (r + 3) / 4 * 4, TW4 = 4 * GF_GAUSS4_THREADS - 2 * HR4;
         a.nstrips = (w + TW4 - 1) / TW4;
         int cta_sm = 4;
@@ -213,7 +213,7 @@ static const char* gf_gauss_launch(const float* src, float* dst, int w, int h, i
             const double cost = (double)((ctas + slots - 1) / slots) * (hb + 2 * r);
             if (cost < best * 0.999) { best = cost; hb4 = hb; }
         }
-        if (const char* e = getenv("GF_GAUSS_HB")) hb4 = atoi(e);
+        hb4 = GF_KNOB("GF_GAUSS_HB", hb4);
         if (hb4 < 1) hb4 = 1;
         if (hb4 > h) hb4 = h;
         a.hb = hb4;

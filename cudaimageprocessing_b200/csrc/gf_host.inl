@@ -84,7 +84,7 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
     // measured on B200 / PCIe Gen5 (4K frame; bench_tools/e2e_check.py, pcie_pipe.py): 1 band 1.89 ms, 2: 1.67, 4: 1.61,
     // 8: 1.75, 16: 1.65 -- chunked copies lose duplex efficiency, so few large bands win (ideal duplex: 1.27 ms)
     nb = nb < 1 ? 1 : (nb > 4 ? 4 : nb);
-    if (const char* e = getenv("GF_HOST_BANDS")) { nb = atoi(e); nb = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb); }
+    nb = GF_KNOB("GF_HOST_BANDS", nb); nb = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
     int up_to = 0;
     for (int b = 0; b < nb; ++b) {
         const int y0 = (int)((int64_t)height * b / nb), y1 = (int)((int64_t)height * (b + 1) / nb);

@@ -2,6 +2,7 @@
 // the kernel-family dispatchers.
 #pragma once
 #include "gf_common.cuh"
+#include "gf_knobs.h"
 
 struct Plane {
     const float* ptr;

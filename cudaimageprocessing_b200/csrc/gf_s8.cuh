@@ -703,9 +703,8 @@ static inline int gf_pick_band_rows(int rows, int r, long nstrips_x_count, long 
 static inline long gf_tape_plan(GfWpArgs& a, int r, long slots, int hb_min, int we_pct)
 {
     a.tape_piece = 0; a.tape_rho = (int)(2.3 * r + 1.0); a.tape_we = we_pct < 100 ? 100 : we_pct;
-    const char* on = getenv("GF_TAPE");
-    if (!on || atoi(on) == 0) return 0;
-    if (const char* e = getenv("GF_TAPE_SLOTS")) slots = atol(e);       // tests / experiments: pieces that span several strips
+    if (GF_KNOB("GF_TAPE", 0) == 0) return 0;
+    slots = GF_KNOB("GF_TAPE_SLOTS", (int)slots);       // tests / experiments: pieces that span several strips
     const bool edges = a.nstrips >= 3 && a.tape_we != 100;
     const long long zi = (long long)(a.tape_rho + a.out_rows) * 100, ze = (long long)(a.tape_rho + a.out_rows) * a.tape_we;
     const long long total = (edges ? 2 * ze + (a.nstrips - 2) * zi : a.nstrips * zi) * a.count;
@@ -734,18 +733,19 @@ static const char* gf_s8_launch(const Job& j)
     a.tape_piece = 0; a.tape_rho = 0; a.tape_we = 100;
     a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
     size_t smem = G::ring_bytes;
-    if (const char* e = getenv("GF_S8_EXTRA_SMEM")) smem += (size_t)atoi(e);      // experiments: lower the residency
+    smem += (size_t)GF_KNOB("GF_S8_EXTRA_SMEM", 0);      // experiments: lower the residency
     // resident warps per SM: the ring in shared memory (228 kB per SM, 1 kB reserved per CTA).  A ring
     // in global memory (L2) would lift this limit but measured 1.6x slower.
     int warps_sm = (int)((size_t)228 * 1024 / (smem + 1024));
     if (warps_sm > 8) warps_sm = 8;
     if (warps_sm < 1) warps_sm = 1;
-    if (const char* e = getenv("GF_S8_WARPS_PER_SM")) warps_sm = atoi(e);
+    warps_sm = GF_KNOB("GF_S8_WARPS_PER_SM", warps_sm);
+    if (warps_sm < 1) warps_sm = 1;
     // Bands: waves of resident warps x (band rows + ramp), see gf_pick_band_rows
     int hb_min = 2 * R + 8;
-    if (const char* e = getenv("GF_S8_HB_MIN")) hb_min = atoi(e);
+    hb_min = GF_KNOB("GF_S8_HB_MIN", hb_min);
     int hb = gf_pick_band_rows(j.out_rows, R, (long)a.nstrips * j.count, (long)sms * warps_sm, hb_min);
-    if (const char* e = getenv("GF_S8_HB")) hb = atoi(e);
+    hb = GF_KNOB("GF_S8_HB", hb);
     if (hb < 1) hb = 1;
     if (hb > j.out_rows) hb = j.out_rows;
     a.hb = hb;
@@ -754,7 +754,7 @@ static const char* gf_s8_launch(const Job& j)
     // they get shorter bands, in proportion.  Measured on B200
     // (profiles/r1_s8_edge_band_pct.txt): 4K r=16 90.9 -> 85.7 us, 8K r=32 515 -> 483 us, 4K r=8 66.2 -> 65.1 us.
     int edge_pct = GF_S8_EDGE_PCT;
-    if (const char* e = getenv("GF_S8_EDGE_PCT")) edge_pct = atoi(e);
+    edge_pct = GF_KNOB("GF_S8_EDGE_PCT", edge_pct);
     a.hb_e = 0; a.nbands_e = 0;
     if (a.nstrips >= 3 && edge_pct > 0 && edge_pct < 100 && a.nbands > 1) {
         const long slots = (long)sms * warps_sm;
@@ -774,7 +774,7 @@ static const char* gf_s8_launch(const Job& j)
     }
     const long per_frame = a.nbands_e > 0 ? 2L * a.nbands_e + (long)(a.nstrips - 2) * a.nbands : (long)a.nstrips * a.nbands;
     long items = per_frame * j.count;
-    if (!getenv("GF_S8_HB"))
+    if (!GF_KNOB_SET("GF_S8_HB"))
         if (const long n = gf_tape_plan(a, R, (long)sms * warps_sm, hb_min, edge_pct > 0 && edge_pct < 100 ? 10000 / edge_pct : 100)) items = n;
     dim3 grid((unsigned)items), block(32);
     constexpr int FIT = (int)((size_t)228 * 1024 / (G::ring_bytes + 1024));
@@ -792,7 +792,7 @@ static const char* gf_s8_try(const Job& j, bool* done, const char** name, bool u
     *done = false;
     if (j.color || j.A.ptr) return nullptr;
     if (j.border == GF_TRUNCATE && ((j.width & 7) || j.width < 256)) return nullptr;
-    if (!u8 && (getenv("GF_DISABLE_S8") || getenv("GF_DISABLE_FAST"))) return nullptr;
+    if (!u8 && (GF_KNOB("GF_DISABLE_S8", 0) || GF_KNOB("GF_DISABLE_FAST", 0))) return nullptr;
     const Plane* pl[3] = {&j.guide, &j.src, &j.dst};
     const uintptr_t amask = u8 ? 7 : 31;                  // one 8-byte / 32-byte vector per lane and row
     for (int i = 0; i < 3; ++i)

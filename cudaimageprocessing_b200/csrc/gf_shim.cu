@@ -1,8 +1,11 @@
 // gf_shim.cu -- C++ drop-in layer: the reference's class GuidedFilter and h* launchers
 // (include/guided_filter.h, include/guided_filter_d.h) implemented on the C ABI.
 // Error behaviour mirrors the reference: unsupported channel combinations print and return
-// (guided_filter_d.cu:893,948,978,1008,1038); CUDA failures print and exit(-1) (cuda_utils.h).
+// (guided_filter_d.cu:893,948,978,1008,1038); CUDA failures print and exit(-1) (cuda_utils.h).  Anything ELSE the
+// library refuses (a shape or radius the reference would have processed) is fatal too: returning would leave the
+// caller's dst unwritten without a sign.
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/gf_b200.h"
 #include "../../include/guided_filter.h"
@@ -13,7 +16,7 @@ namespace {
 void handle(int rc, const char* where)
 {
     if (rc == GF_OK) return;
-    if (rc == GF_ERR_UNSUPPORTED) {
+    if (rc == GF_ERR_UNSUPPORTED && std::strstr(gf_last_error(), "Do not support channel")) {
         std::printf("%s\n", gf_last_error());
         return;
     }
@@ -89,11 +92,10 @@ void hLinearTransform(float* src, float* dst, float* a, float* b, const int4& sw
 void hGuidedFilter(float* d_guided, float* d_src, float* d_dst, float* d_A, float* d_B, float eps, int radius, int width,
                    int height, int stride)
 {
-    // d_A / d_B are caller-owned SCRATCH in the reference (its two kernels hand a, b over through
-    // them, guided_filter_d.cu:1047-1093; main.cpp never reads them back).  The fused kernel keeps
-    // a, b on chip, so by default they are left untouched -- writing them costs 8 B/px of HBM traffic
-    // and the slower kernel family.  GF_SHIM_FILL_AB=1 fills them for callers that do look.
-    static const bool fill_ab = [] { const char* e = std::getenv("GF_SHIM_FILL_AB"); return e && std::atoi(e) != 0; }();
+    // The reference's two kernels hand a, b over through d_A / d_B (guided_filter_d.cu:1047-1093) and main.cpp:283-286
+    // reads them back, so they are filled by default (the producer warps of the fused kernel store them on the
+    // side: 8 B/px of extra HBM writes).  GF_SHIM_SKIP_AB=1 leaves them untouched for callers that never look.
+    static const bool fill_ab = [] { const char* e = std::getenv("GF_SHIM_SKIP_AB"); return !(e && std::atoi(e) != 0); }();
     handle(gf_guided_gray(d_guided, d_src, d_dst, fill_ab ? d_A : nullptr, fill_ab ? d_B : nullptr, width, height, stride, stride,
                           stride, stride, radius, eps, GF_BORDER_REFLECT101, nullptr),
            "hGuidedFilter");

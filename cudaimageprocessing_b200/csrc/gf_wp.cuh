@@ -481,9 +481,9 @@ static const char* gf_wp_launch(const Job& j)
     // the 128-register build of the K=4 kernel holds 16 warps: better when the job spans many waves
     const long min_items = (long)a.nstrips * ((j.out_rows + 255) / 256) * j.count;
     bool big = K == 4 && R <= 8 && min_items > (long)sms * 12;
-    if (const char* e = getenv("GF_WP_BIG")) big = K == 4 && R <= 8 && atoi(e) != 0;
+    if (GF_KNOB_SET("GF_WP_BIG")) big = K == 4 && R <= 8 && GF_KNOB("GF_WP_BIG", 0) != 0;
     int warps_target = sms * (big ? 16 : warps_sm);
-    if (const char* e = getenv("GF_WP_WARPS_PER_SM")) warps_target = sms * atoi(e);
+    if (GF_KNOB_SET("GF_WP_WARPS_PER_SM")) warps_target = sms * GF_KNOB("GF_WP_WARPS_PER_SM", 1);
     // Bands: as many as fit in ONE wave of resident warps (a partial second wave costs more than
     // its share), but never so short that the 4R warm-up rows dominate; large jobs get many
     // waves of hb_max-row bands instead.
@@ -491,7 +491,7 @@ static const char* gf_wp_launch(const Job& j)
     if (nb < 1) nb = 1;
     int hb = (j.out_rows + nb - 1) / nb;
     int hb_min = 4 * R, hb_max = 256;
-    if (const char* e = getenv("GF_WP_HB_MIN")) hb_min = atoi(e);
+    hb_min = GF_KNOB("GF_WP_HB_MIN", hb_min);
     if (hb < hb_min) hb = hb_min;
     if (hb > hb_max) hb = hb_max;
     if (hb > j.out_rows) hb = j.out_rows;
@@ -515,7 +515,7 @@ static const char* gf_wp_try(const Job& j, bool* done, const char** name)
 {
     *done = false;
     if (j.color || j.r < 1 || j.r > 16) return nullptr;
-    if (getenv("GF_DISABLE_WP") || getenv("GF_DISABLE_FAST")) return nullptr;
+    if (GF_KNOB("GF_DISABLE_WP", 0) || GF_KNOB("GF_DISABLE_FAST", 0)) return nullptr;
     const Plane* pl[3] = {&j.guide, &j.src, &j.dst};
     for (int i = 0; i < 3; ++i)
         if (pl[i]->channels != 1 || pl[i]->coff != 0 || (pl[i]->stride & 3) || (pl[i]->frame_stride & 3) ||

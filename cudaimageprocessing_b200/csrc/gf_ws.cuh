@@ -58,15 +58,34 @@ struct GfWsGeom {
     static constexpr int RING = 2 * R + 2;               // a/b rows per stream
     static constexpr int ROW_F4 = (K / 2) * 32;          // float4 per ring row: [pair of columns][lane] = (a0, b0, a1, b1)
     static constexpr size_t ring_bytes = (size_t)RING * ROW_F4 * 16;
-    static constexpr size_t smem_bytes = (size_t)NS * ring_bytes + 128;   // + the 2 NS row counters
+    static constexpr size_t ctrl_bytes = 64 + (size_t)NS * RING * 8;      // 2 NS row counters + one mbarrier per ring slot
+    static constexpr size_t smem_bytes = (size_t)NS * ring_bytes + (ctrl_bytes + 127) / 128 * 128;
     static constexpr int MIN_SUB = R + 1;                // shortest sub-band whose neighbours can share rows with it
 };
 
 // ---- hand-off primitives --------------------------------------------------------------------------
+// GF_WS_SYNC: how a consumer learns that an a/b row is in the ring.
+//   2 (default)  one mbarrier per ring slot (phase = use count of the slot): the producer's lane 0 arrives
+//                (release at CTA scope, no MEMBAR), consumers sleep in mbarrier.try_wait (hardware wake-up);
+//   1            monotonic row counter, st.release / ld.acquire, consumers spin;
+//   0            same counter with a nanosleep back-off (first version: the sleep quantum turned out to be
+//                longer than a row, profiles/r2_ws_sync_variants.jsonl).
+// The consumed-rows counter (consumer -> producer) is a counter in every variant: a producer reads it once
+// per row and practically never has to wait (the consumer releases a ring row as soon as it is in registers).
+#ifndef GF_WS_SYNC
+#define GF_WS_SYNC 2
+#endif
 #ifdef GF_CPU_EMU
 static inline int gf_ws_ld_acq(const volatile int* p) { return *p; }
 static inline void gf_ws_st_rel(volatile int* p, int v) { *p = v; }
 static inline void gf_ws_pause() { emu::yield_to_scheduler(emu::RUNNABLE); }
+// emulated mbarrier: the word counts completed phases
+static inline void gf_ws_bar_init(unsigned long long* b) { *b = 0; }
+static inline void gf_ws_bar_arrive(unsigned long long* b) { *(volatile unsigned long long*)b = *b + 1; }
+static inline void gf_ws_bar_wait(const unsigned long long* b, int phase)
+{
+    while (*(const volatile unsigned long long*)b <= (unsigned long long)phase) gf_ws_pause();
+}
 #else
 __device__ __forceinline__ int gf_ws_ld_acq(const volatile int* p)
 {
@@ -78,7 +97,30 @@ __device__ __forceinline__ void gf_ws_st_rel(volatile int* p, int v)
 {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(const_cast<int*>(p))), "r"(v) : "memory");
 }
-__device__ __forceinline__ void gf_ws_pause() { __nanosleep(32); }
+__device__ __forceinline__ void gf_ws_pause()
+{
+#if GF_WS_SYNC == 0
+    __nanosleep(32);
+#endif
+}
+__device__ __forceinline__ void gf_ws_bar_init(unsigned long long* b)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void gf_ws_bar_arrive(unsigned long long* b)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void gf_ws_bar_wait(const unsigned long long* b, int phase)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(const_cast<unsigned long long*>(b));
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "GF_WS_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra GF_WS_WAIT_%=;\n\t}"
+        ::"r"(addr), "r"((unsigned)(phase & 1)) : "memory");
+}
 #endif
 __device__ __forceinline__ void gf_ws_wait(const volatile int* ctr, int need)
 {
@@ -88,6 +130,26 @@ __device__ __forceinline__ void gf_ws_publish(volatile int* ctr, int val, int la
 {
     __syncwarp();                       // every lane's ring accesses are ordered before lane 0's release
     if (lane == 0) gf_ws_st_rel(ctr, val);
+}
+// row `idx` (count from the stream's first own row) of a stream is in its ring
+template <int RING>
+__device__ __forceinline__ void gf_ws_row_ready(volatile int* prod, unsigned long long* bars, int idx, int slot, int lane)
+{
+#if GF_WS_SYNC == 2
+    __syncwarp();
+    if (lane == 0) gf_ws_bar_arrive(bars + slot);
+#else
+    gf_ws_publish(prod, idx + 1, lane);
+#endif
+}
+template <int RING>
+__device__ __forceinline__ void gf_ws_row_wait(const volatile int* prod, const unsigned long long* bars, int idx)
+{
+#if GF_WS_SYNC == 2
+    gf_ws_bar_wait(bars + idx % RING, idx / RING);
+#else
+    gf_ws_wait(prod, idx + 1);
+#endif
 }
 
 // ---- (2R+1)-window sums of K adjacent columns per lane, on packed quantity pairs --------------------
@@ -235,10 +297,20 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
         const int64_t ro = (int64_t)rr * stride;
         if (vec) {
             const float* rp = planex + ro;
+            if (K % 8 == 0) {              // one 32-byte access per 8 columns: lane stride = access size, fully coalesced
 #pragma unroll
-            for (int c = 0; c < K / 4; ++c) {
-                const float4 t = *reinterpret_cast<const float4*>(rp + 4 * c);
-                v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+                for (int c = 0; c < K / 8; ++c) {
+                    float2 t[4];
+                    gf_ld8(rp + 8 * c, t);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { v[8 * c + 2 * i] = t[i].x; v[8 * c + 2 * i + 1] = t[i].y; }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < K / 4; ++c) {
+                    const float4 t = *reinterpret_cast<const float4*>(rp + 4 * c);
+                    v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+                }
             }
         } else if (EDGE) {
             const float* rp = plane + ro;
@@ -295,6 +367,7 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
     const float epsNN = a.eps * Nf * Nf;
     const GfNorm nk = gf_norm_make(Nf);
     volatile int* prod = ctrl + 2 * k;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(const_cast<int*>(ctrl) + 16);
     const volatile int* cons_own = ctrl + 2 * k + 1;
     const volatile int* cons_sp = ctrl + 2 * (st.sp >= 0 ? st.sp : k) + 1;
     const int n_last = st.L - 1 + R;
@@ -379,7 +452,7 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
 #pragma unroll
             for (int c = 0; c < K / 2; ++c) rp[c * 32] = make_float4(av[2 * c], bv[2 * c], av[2 * c + 1], bv[2 * c + 1]);
         }
-        gf_ws_publish(prod, idx + 1, lane);
+        gf_ws_row_ready<RING>(prod, bars + k * RING, idx, slot, lane);
         slot = slot + 1 == RING ? 0 : slot + 1;
         // ---- optional A / B planes (hGuidedFilter's d_A, d_B): own territory rows, output columns ----
         if (a.A != nullptr && m >= 0 && m < st.L) {
@@ -430,13 +503,15 @@ __device__ __forceinline__ void gf_ws_stage2(const GfWsArgs& a, const GfWsPlan<N
     const int ep_last = st.ep >= 0 ? pl.s[st.ep].L - 1 - pl.s[st.ep].m0 + st.L : 0;    // ring index of row n >= L in the end partner: ep_last - n
 
     // ring row and producer counter of stream-local a/b row n
-    auto resolve = [&](int n, const float4*& base, const volatile int*& prod, int& idx) {
+    const unsigned long long* bars = reinterpret_cast<const unsigned long long*>(const_cast<const int*>(ctrl) + 16);
+    auto resolve = [&](int n, const float4*& base, const volatile int*& prod, const unsigned long long*& bar, int& idx) {
         int t = k;
         idx = n - st.m0;
         if (n < 0 && st.sp >= 0) { t = st.sp; idx = -1 - n; }              // (a shared start: the partner's m0 is 0)
         else if (n >= st.L && st.ep >= 0) { t = st.ep; idx = ep_last - n; }
         base = rings + (t * RING + idx % RING) * G::ROW_F4 + lane;
         prod = ctrl + 2 * t;
+        bar = bars + t * RING;
     };
     auto ld_guide = [&](int i, float (&g)[K]) {
         const int y = st.ys + st.d * i;
@@ -457,15 +532,15 @@ __device__ __forceinline__ void gf_ws_stage2(const GfWsArgs& a, const GfWsPlan<N
     const int n_last = st.L - 1 + R;
 #pragma unroll 1
     for (int n = -R; n <= n_last; ++n) {
-        const float4* nb; const volatile int* np; int ni;
-        resolve(n, nb, np, ni);
-        gf_ws_wait(np, ni + 1);
+        const float4* nb; const volatile int* np; const unsigned long long* nbar; int ni;
+        resolve(n, nb, np, nbar, ni);
+        gf_ws_row_wait<RING>(np, nbar, ni);
         float4 nw[K / 2];
 #pragma unroll
         for (int c = 0; c < K / 2; ++c) nw[c] = nb[c * 32];
         if (n - KW >= -R) {
-            const float4* ob; const volatile int* op; int oi;
-            resolve(n - KW, ob, op, oi);
+            const float4* ob; const volatile int* op; const unsigned long long* obar; int oi;
+            resolve(n - KW, ob, op, obar, oi);
 #pragma unroll
             for (int c = 0; c < K / 2; ++c) {
                 const float4 o = ob[c * 32];
@@ -530,6 +605,7 @@ __global__ void __launch_bounds__(64 * NS, 1) gf_ws_gray_kernel(const GF_GRID_CO
     const int y0 = a.out_y0 + band * a.hb;
     const int y1 = y0 + a.hb < a.out_y0 + a.out_rows ? y0 + a.hb : a.out_y0 + a.out_rows;
     if (threadIdx.x < 2 * NS) ctrl[threadIdx.x] = 0;
+    if (threadIdx.x < NS * G::RING) gf_ws_bar_init(reinterpret_cast<unsigned long long*>(const_cast<int*>(ctrl) + 16) + threadIdx.x);
     __syncthreads();
     GfWsPlan<NS> pl;
     gf_ws_plan<R, NS>(y0, y1, pl);
@@ -548,26 +624,13 @@ __global__ void __launch_bounds__(64 * NS, 1) gf_ws_gray_kernel(const GF_GRID_CO
 // ---- host side --------------------------------------------------------------------------------------
 #ifndef GF_NO_HOST
 // Longest sub-band a stream walks with sliding (add / subtract) vertical sums before the band is cut.
+// Whether gf_guided_gray & co. take this kernel when they can (option GF_WS overrides)
+#ifndef GF_WS_DEFAULT
+#define GF_WS_DEFAULT 0
+#endif
 #ifndef GF_WS_MAX_SUB
 #define GF_WS_MAX_SUB 512
 #endif
-
-struct GfWsTune {          // developer knobs, read ONCE (first launch); nothing here changes results
-    int disable;           // GF_DISABLE_WS=1: hand every job to the older kernels
-    int k;                 // GF_WS_K = 8 / 12 / 16: force a column count (default: per radius)
-    int hb;                // GF_WS_HB: force the band height
-};
-static inline const GfWsTune& gf_ws_tune()
-{
-    static const GfWsTune t = [] {
-        GfWsTune v{0, 0, 0};
-        if (const char* e = getenv("GF_DISABLE_WS")) v.disable = atoi(e);
-        if (const char* e = getenv("GF_WS_K")) v.k = atoi(e);
-        if (const char* e = getenv("GF_WS_HB")) v.hb = atoi(e);
-        return v;
-    }();
-    return t;
-}
 
 // Band height: CTAs run in waves of `sms` (one CTA per SM); a CTA's time ~ its slowest stream:
 //   (hb + 2 x 0.85 R outer rows) / NS  +  2R warm-up rows at ~0.2  +  ~2 rows of start-up.
@@ -605,7 +668,7 @@ static const char* gf_ws_launch(const Job& j)
     a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
     a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
     int hb = gf_ws_pick_band<R, NS>(j.out_rows, (long)a.nstrips * j.count, sms);
-    if (gf_ws_tune().hb > 0) hb = gf_ws_tune().hb;
+    hb = GF_KNOB("GF_WS_HB", hb);
     if (hb > j.out_rows) hb = j.out_rows;
     if (hb < 1) hb = 1;
     a.hb = hb;
@@ -628,8 +691,8 @@ static const char* gf_ws_launch(const Job& j)
 static const char* gf_ws_try(const Job& j, bool* done, const char** name)
 {
     *done = false;
-    const GfWsTune& tn = gf_ws_tune();
-    if (tn.disable || j.color) return nullptr;
+    if (j.color || !GF_KNOB("GF_WS", GF_WS_DEFAULT) || GF_KNOB("GF_DISABLE_FAST", 0)) return nullptr;
+    const int force_k = GF_KNOB("GF_WS_K", 0);
     if ((j.A.ptr == nullptr) != (j.B.ptr == nullptr)) return nullptr;
     const Plane* pl[5] = {&j.guide, &j.src, &j.dst, &j.A, &j.B};
     for (int i = 0; i < 5; ++i) {
@@ -639,10 +702,13 @@ static const char* gf_ws_try(const Job& j, bool* done, const char** name)
     }
     if (j.A.ptr && (j.A.stride != j.B.stride || j.A.frame_stride != j.B.frame_stride)) return nullptr;
     if (j.width & 3) return nullptr;
+    // K = 8 / 16 read the two input planes with 32-byte accesses
+    const bool in32 = !((j.guide.stride | j.src.stride | j.guide.frame_stride | j.src.frame_stride) & 7) &&
+                      !(((uintptr_t)j.guide.ptr | (uintptr_t)j.src.ptr) & 31);
     // single reflections only (rows), and bands tall enough for at least one stream with its ramp
     if (j.height < 4 * j.r + 2 || j.out_rows < 1) return nullptr;
 #define GF_WS_CASE(RR, KK, NN, NAME)                                                  \
-    if (j.r == RR && (tn.k == 0 || tn.k == KK) && j.width >= GfWsGeom<RR, KK, NN>::WOUT) { \
+    if (j.r == RR && (force_k == 0 || force_k == KK) && j.width >= GfWsGeom<RR, KK, NN>::WOUT && (KK % 8 != 0 || in32)) { \
         *done = true; *name = NAME; return gf_ws_launch<RR, KK, NN>(j);              \
     }
 #ifdef GF_CPU_EMU

@@ -183,6 +183,13 @@ int gf_gaussian_gray(const float* src, float* dst, int width, int height, int64_
 const char* gf_last_kernel(void);
 int64_t gf_launch_count(void);
 
+/* Developer / test options of the launch paths (kernel family, band height, residency: names in
+   DESIGN.md section 8, e.g. "GF_DISABLE_WS", "GF_WS_K", "GF_S8_HB").  No option changes results.
+   The library never reads the environment on a launch: an option is seeded ONCE, when a launch
+   path first looks at it, from the environment variable of the same name, and this call overrides
+   it from then on.  value >= 0 sets it, value < 0 restores the built-in default. */
+int gf_set_option(const char* name, int value);
+
 #ifdef __cplusplus
 }
 #endif

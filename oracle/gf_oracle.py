@@ -199,19 +199,6 @@ def to_u8(q) -> np.ndarray:
     return np.clip(np.rint(v), 0, 255).astype(np.uint8)
 
 
-def integral_u8(img_u8: np.ndarray, wrap32: bool = False) -> np.ndarray:
-    """Inclusive summed-area table of a uint8 image in int64 (exact).
-
-    Follows Integral/integral_d.cu:863-893 (`hIntegral`; output W x H, no zero
-    row/column -- Integral/main.cpp:124 compares against cv::integral's
-    interior).  wrap32=True reduces mod 2^32 like the reference's int32 output.
-    """
-    s = np.cumsum(np.cumsum(np.asarray(img_u8, dtype=np.int64), axis=0), axis=1)
-    if wrap32:
-        s = s.astype(np.uint32).astype(np.int32)
-    return s
-
-
 def box_sum_u8(img_u8: np.ndarray, r: int, mode: int) -> np.ndarray:
     """Exact integer (int64) window sums of a uint8 image."""
     a = np.asarray(img_u8, dtype=np.int64)
@@ -229,6 +216,76 @@ def box_sum_u8(img_u8: np.ndarray, r: int, mode: int) -> np.ndarray:
         return np.moveaxis(c[2 * r + 1: 2 * r + 1 + n] - c[0:n], 0, axis)
 
     return axis_sum(axis_sum(a, 1), 0)
+
+
+# ---- the four element-wise launchers of path A ----------------------------------
+# float32 restatements of guided_filter_d.cu:273-412 as driven by hMultiply / hCalcA / hCalcB /
+# hLinearTransform (:927-1044).  "Guide-shaped" operands have the source's channel count or ONE channel
+# (the reference's CN1 kernels broadcast them over the source channels).
+def _fma32(a, b, c):
+    """__fmaf_rn on float32 operands (the float64 product of two float32 values is exact)."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def _bcast(g, like):
+    g = np.asarray(g, np.float32)
+    like = np.asarray(like)
+    if like.ndim == 3 and g.ndim == 2:
+        return np.repeat(g[:, :, None], like.shape[2], axis=2)
+    return g
+
+
+def pw_multiply(a, b):
+    """hMultiply: c = __fmul_rn(a, b) (gMultiply :273-287 / gMultiplyCN1 :290-303)."""
+    a = np.asarray(a, np.float32)
+    return (a * _bcast(b, a)).astype(np.float32)
+
+
+def pw_calc_a(pm, im, ipm, iim, eps):
+    """hCalcA: a = fma(pm, -im, ipm) / fma(-im, im, iim + eps); eps joins iim BEFORE im^2 is subtracted
+    (gCalcA :306-323, gCalcACN1 :326-346)."""
+    pm = np.asarray(pm, np.float32)
+    vim = _bcast(im, pm)
+    viim = (_bcast(iim, pm) + np.float32(eps)).astype(np.float32)
+    num = _fma32(pm, -vim, np.asarray(ipm, np.float32))
+    den = _fma32(-vim, vim, viim)
+    return (num / den).astype(np.float32)
+
+
+def pw_calc_b(a, pm, im):
+    """hCalcB: b = fma(a, -im, pm) (gCalcB :349-362).  The reference's 1-channel-guide variant truncates -im
+    to int and reads im at the source index (gCalcBCN1 :371-372): that bug is NOT reproduced, the CN1 case
+    broadcasts im like the other CN1 kernels."""
+    a = np.asarray(a, np.float32)
+    return _fma32(a, -_bcast(im, a), np.asarray(pm, np.float32))
+
+
+def pw_linear_transform(src, a, b):
+    """hLinearTransform: dst = fma(src, a, b), src guide-shaped (gLinearTransform :382-395 / CN1 :398-412)."""
+    a = np.asarray(a, np.float32)
+    return _fma32(_bcast(src, a), a, np.asarray(b, np.float32))
+
+
+def class_run_steps(I, p, r: int, eps: float):
+    """`GuidedFilter::run` step by step (guided_filter.cpp:28-66) with every intermediate plane, float32
+    element-wise steps around float64-accurate TRUNCATE box means rounded to float32 (the reference's float32
+    integral image is NOT reproduced: SURVEY fact 4)."""
+    I = np.asarray(I, np.float32)
+    p = np.asarray(p, np.float32)
+    bm_ = lambda x: box_mean(x, r, BORDER_TRUNCATE, np.float64).astype(np.float32)
+    s = {}
+    s["pm"] = bm_(p)
+    s["im"] = bm_(I)
+    s["ip"] = pw_multiply(p, I)
+    s["ii"] = pw_multiply(I, I)
+    s["ipm"] = bm_(s["ip"])
+    s["iim"] = bm_(s["ii"])
+    s["a"] = pw_calc_a(s["pm"], s["im"], s["ipm"], s["iim"], eps)
+    s["b"] = pw_calc_b(s["a"], s["pm"], s["im"])
+    s["am"] = bm_(s["a"])
+    s["bm"] = bm_(s["b"])
+    s["q"] = pw_linear_transform(I, s["am"], s["bm"])
+    return s
 
 
 # ---- Integral/ module (SURVEY 8(f) rank 1) ---------------------------------------------------------

@@ -62,3 +62,17 @@ def synth_pair(h, w, seed=0, kind="noise"):
         I = np.clip(I + rng.normal(0, 0.02, (h, w)).astype(np.float32), 0, 1).astype(np.float32)
         p = np.clip(I * 0.8 + 0.1 + rng.normal(0, 0.05, (h, w)).astype(np.float32), 0, 1).astype(np.float32)
     return I, p
+
+
+@pytest.fixture
+def knob():
+    """Sets launch-path options through the C ABI (gf_set_option) for one test and restores the defaults:
+    knob(be, "GF_S8_HB", 40).  (The library does not read the environment per launch.)"""
+    done = []
+
+    def _set(be, name, value):
+        be.api.set_option(name, value)
+        done.append((be, name))
+    yield _set
+    for be, name in done:
+        be.api.set_option(name, -1)

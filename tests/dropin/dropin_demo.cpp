@@ -6,7 +6,9 @@
 // drop-in at the source level.  Usage: dropin_demo <in.bin> <out.bin>
 //   in.bin : int32 w, h, r, sch; float eps; float guide[h*w]; float src[h*w*sch]
 //   out.bin: float q_class[h*w*sch] (GuidedFilter::run); float q_fused[h*w], A[h*w], B[h*w]
-//            (hGuidedFilter on channel 0 of src)
+//            (hGuidedFilter on channel 0 of src); float q_chain[h*w*sch] (the eleven launcher calls of
+//            GuidedFilter::run, guided_filter.cpp:28-66, made by hand: hBoxFilter, hMultiply, hCalcA, hCalcB,
+//            hLinearTransform on cudaMallocPitch planes with the reference's int4 whcs descriptors)
 #include <cstdio>
 #include <memory>
 #include <vector>
@@ -46,6 +48,38 @@ int main(int argc, char** argv)
     std::vector<float> q_class((size_t)w * h * sch);
     CHECK(cudaMemcpy2D(q_class.data(), spitch1, d_dst, spitch2, spitch1, h, cudaMemcpyDeviceToHost));
 
+    // --- the body of GuidedFilter::run (guided_filter.cpp:57-65) launcher by launcher, scratch planes as in
+    //     allocMemory (guided_filter.cpp:70-93): int4 = {.x height, .y channels, .z stride, .w width}
+    std::vector<float> q_chain((size_t)w * h * sch);
+    {
+        int4 swhcs, gwhcs, iwhcs;
+        swhcs.w = w; swhcs.x = h; swhcs.y = sch; swhcs.z = static_cast<int>(spitch2 / sizeof(float));
+        gwhcs.w = w; gwhcs.x = h; gwhcs.y = 1; gwhcs.z = static_cast<int>(gpitch2 / sizeof(float));
+        iwhcs.w = w + 1; iwhcs.x = h + 1; iwhcs.y = sch; iwhcs.z = 0;
+        float *pm, *im, *ipm, *iim, *a, *b, *am, *bm, *d_chain;
+        size_t ps = 0, pg = 0;
+        float** splanes[] = {&pm, &ipm, &a, &b, &am, &bm, &d_chain};
+        for (float** pp : splanes) CHECK(cudaMallocPitch(reinterpret_cast<void**>(pp), &ps, spitch1, h));
+        CHECK(cudaMallocPitch(reinterpret_cast<void**>(&im), &pg, gpitch1, h));
+        CHECK(cudaMallocPitch(reinterpret_cast<void**>(&iim), &pg, gpitch1, h));
+        if (ps != spitch2 || pg != gpitch2) return 7;
+        hBoxFilter(d_src, pm, nullptr, swhcs, iwhcs, r);
+        hBoxFilter(d_guidiance, im, nullptr, gwhcs, iwhcs, r);
+        hMultiply(d_src, d_guidiance, ipm, swhcs, gwhcs);
+        hMultiply(d_guidiance, d_guidiance, iim, gwhcs, gwhcs);
+        hBoxFilter(ipm, ipm, nullptr, swhcs, iwhcs, r);
+        hBoxFilter(iim, iim, nullptr, gwhcs, iwhcs, r);
+        hCalcA(a, pm, im, ipm, iim, swhcs, gwhcs, eps);
+        hCalcB(b, a, pm, im, swhcs, gwhcs);
+        hBoxFilter(a, am, nullptr, swhcs, iwhcs, r);
+        hBoxFilter(b, bm, nullptr, swhcs, iwhcs, r);
+        hLinearTransform(d_guidiance, d_chain, am, bm, gwhcs, swhcs);
+        CHECK(cudaDeviceSynchronize());
+        CHECK(cudaMemcpy2D(q_chain.data(), spitch1, d_chain, spitch2, spitch1, h, cudaMemcpyDeviceToHost));
+        for (float** pp : splanes) CUDA_SAFE_FREE(*pp);
+        CUDA_SAFE_FREE(im); CUDA_SAFE_FREE(iim);
+    }
+
     // --- path B call sequence (main.cpp:215-279) on channel 0 of src
     std::vector<float> src0((size_t)w * h);
     for (size_t i = 0; i < src0.size(); ++i) src0[i] = src[i * sch];
@@ -72,6 +106,7 @@ int main(int argc, char** argv)
     std::fwrite(q.data(), 4, q.size(), f);
     std::fwrite(A.data(), 4, A.size(), f);
     std::fwrite(B.data(), 4, B.size(), f);
+    std::fwrite(q_chain.data(), 4, q_chain.size(), f);
     std::fclose(f);
     CUDA_SAFE_FREE(d_src); CUDA_SAFE_FREE(d_guidiance); CUDA_SAFE_FREE(d_dst);
     CUDA_SAFE_FREE(d_s); CUDA_SAFE_FREE(d_g); CUDA_SAFE_FREE(d_q); CUDA_SAFE_FREE(d_A); CUDA_SAFE_FREE(d_B);

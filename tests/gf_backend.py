@@ -107,10 +107,58 @@ class _Base:
         self.sync()
         return self.down(o)
 
-    def pointwise(self, name, out_shape, *arrays, tail=()):
-        bufs = [self.up(a) for a in arrays]
-        o = self.empty(out_shape)
-        return bufs, o
+    # --- the four element-wise launchers of path A (hMultiply, hCalcA, hCalcB, hLinearTransform) ---
+    @staticmethod
+    def _ch(a):
+        return 1 if np.ndim(a) == 2 else np.shape(a)[2]
+
+    def multiply(self, a, b):
+        h, w = a.shape[:2]
+        da, db = self.up(a), self.up(b)
+        o = self.empty(a.shape)
+        self.api.call("gf_multiply", self.ptr(da), self.ptr(db), self.ptr(o), w, h, self._ch(a), self._ch(b), 0, 0, None)
+        self.sync()
+        return self.down(o)
+
+    def calc_a(self, pm, im, ipm, iim, eps):
+        h, w = pm.shape[:2]
+        d = [self.up(x) for x in (pm, im, ipm, iim)]
+        o = self.empty(pm.shape)
+        self.api.call("gf_calc_a", self.ptr(o), self.ptr(d[0]), self.ptr(d[1]), self.ptr(d[2]), self.ptr(d[3]), w, h,
+                      self._ch(pm), self._ch(im), 0, 0, eps, None)
+        self.sync()
+        return self.down(o)
+
+    def calc_b(self, a, pm, im):
+        h, w = a.shape[:2]
+        d = [self.up(x) for x in (a, pm, im)]
+        o = self.empty(a.shape)
+        self.api.call("gf_calc_b", self.ptr(o), self.ptr(d[0]), self.ptr(d[1]), self.ptr(d[2]), w, h, self._ch(a), self._ch(im),
+                      0, 0, None)
+        self.sync()
+        return self.down(o)
+
+    def linear_transform(self, src, a, b):
+        h, w = a.shape[:2]
+        d = [self.up(x) for x in (src, a, b)]
+        o = self.empty(a.shape)
+        self.api.call("gf_linear_transform", self.ptr(d[0]), self.ptr(o), self.ptr(d[1]), self.ptr(d[2]), w, h, self._ch(a),
+                      self._ch(src), 0, 0, None)
+        self.sync()
+        return self.down(o)
+
+    def class_run_by_launchers(self, I, p, r, eps):
+        """The eleven launcher calls of GuidedFilter::run (guided_filter.cpp:28-66), in its order, through the C ABI."""
+        pm = self.box(p, r, 1)
+        im = self.box(I, r, 1)
+        ipm = self.box(self.multiply(p, I), r, 1)
+        iim = self.box(self.multiply(I, I), r, 1)
+        a = self.calc_a(pm, im, ipm, iim, eps)
+        b = self.calc_b(a, pm, im)
+        am = self.box(a, r, 1)
+        bm = self.box(b, r, 1)
+        return {"pm": pm, "im": im, "ipm": ipm, "iim": iim, "a": a, "b": b, "am": am, "bm": bm,
+                "q": self.linear_transform(I, am, bm)}
 
 
 class EmuBackend(_Base):

@@ -130,7 +130,7 @@ def test_color_1080p_r16(be, border):
     assert err <= TOL
 
 
-def test_fuzz_s8_against_generic_kernel(be, monkeypatch):
+def test_fuzz_s8_against_generic_kernel(be, knob):
     """Differential fuzz: 150 random (shape, radius, border, row padding) jobs through the tuned kernels
     and through the generic kernel (a different algorithm: thread per column, scan-based window sums).
     Catches geometry corner cases (strip/band boundaries, which strip mode an edge strip takes...)."""
@@ -149,9 +149,9 @@ def test_fuzz_s8_against_generic_kernel(be, monkeypatch):
         q1, q0 = torch.empty_like(I), torch.empty_like(I)
         be.api.call("gf_guided_gray", I.data_ptr(), p.data_ptr(), q1.data_ptr(), None, None, w, h, s_, s_, s_, 0, r, 1e-2, border, None)
         k1 = be.api.last_kernel()
-        monkeypatch.setenv("GF_DISABLE_FAST", "1")
+        knob(be, "GF_DISABLE_FAST", 1)
         be.api.call("gf_guided_gray", I.data_ptr(), p.data_ptr(), q0.data_ptr(), None, None, w, h, s_, s_, s_, 0, r, 1e-2, border, None)
-        monkeypatch.delenv("GF_DISABLE_FAST")
+        knob(be, "GF_DISABLE_FAST", -1)
         torch.cuda.synchronize()
         assert be.api.last_kernel().startswith("generic")
         d = float((q1[:, :w] - q0[:, :w]).abs().max())
@@ -160,7 +160,7 @@ def test_fuzz_s8_against_generic_kernel(be, monkeypatch):
     print(f"fuzz: worst |tuned - generic| = {worst:.2e}")
 
 
-def test_fuzz_c4_against_generic_kernel(be, monkeypatch):
+def test_fuzz_c4_against_generic_kernel(be, knob):
     """The same differential fuzz for the tuned colour-guide kernel (batches of 1-3 frames)."""
     import torch
     rng = np.random.default_rng(77)
@@ -177,9 +177,9 @@ def test_fuzz_c4_against_generic_kernel(be, monkeypatch):
         args = (n, w, h, 3, 0, 0, 0, 0, 0, 0, r, 1e-2, 0, None)
         be.api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q1.data_ptr(), *args)
         assert be.api.last_kernel() == f"c4_r{r}"
-        monkeypatch.setenv("GF_DISABLE_FAST", "1")
+        knob(be, "GF_DISABLE_FAST", 1)
         be.api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q0.data_ptr(), *args)
-        monkeypatch.delenv("GF_DISABLE_FAST")
+        knob(be, "GF_DISABLE_FAST", -1)
         torch.cuda.synchronize()
         assert be.api.last_kernel() == "generic_color"
         d = float((q1 - q0).abs().max())
@@ -229,17 +229,17 @@ def test_no_out_of_bounds_access(be):
             assert torch.isnan(vQ[:, w:]).all() and torch.isnan(bQ[:G]).all() and torch.isnan(bQ[G + h:]).all(), (h, w, r)
 
 
-def test_long_bands_do_not_drift(be, monkeypatch):
+def test_long_bands_do_not_drift(be, knob):
     """Large batches / tall strips make the band chooser pick full-height bands: the running sums
     then run for the whole image (colour: no re-seed; gray: re-seeded every 2r+1 rows)."""
     I3 = np.random.default_rng(100).random((1080, 1920, 3), dtype=np.float32)
     p = np.random.default_rng(10000).random((1080, 1920), dtype=np.float32)
-    monkeypatch.setenv("GF_C4_HB", "1080")
+    knob(be, "GF_C4_HB", 1080)
     q = be.guided_color(I3, p, 16, 1e-2, 0)
     assert be.api.last_kernel() == "c4_r16"
     assert np.abs(q - C.guided_color_f32(I3, p, 16, 1e-2, 0, NT)).max() <= 2e-5
     I, p = synth_pair(2160, 3840, seed=0)
-    monkeypatch.setenv("GF_S8_HB", "2160")
+    knob(be, "GF_S8_HB", 2160)
     q = be.guided_gray(I, p, 8, 1e-2, 0)
     assert be.api.last_kernel() == "s8_r8"
     assert np.abs(q - C.guided_gray_f64(I, p, 8, 1e-2, 0, NT)).max() <= 2e-6
@@ -386,17 +386,21 @@ def test_host_entry_and_dropin_program(be, tmp_path):
         f.write(s.tobytes())
     n = w * h
     rq, ra, rb = O.guided_filter_gray(g, s[:, :, 0], r, eps, 0, np.float64, return_ab=True)
-    for fill_ab in (False, True):
+    for skip_ab in (False, True):
         env = dict(os.environ)
-        if fill_ab:
-            env["GF_SHIM_FILL_AB"] = "1"        # hGuidedFilter's d_A / d_B are scratch: written only on request
+        if skip_ab:
+            env["GF_SHIM_SKIP_AB"] = "1"        # opt-out: hGuidedFilter's d_A / d_B stay untouched
         subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], env=env)
         out = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
         q_class = out[:n * sch].reshape(h, w, sch)
         q_fused, A, B = (out[n * sch + i * n: n * sch + (i + 1) * n].reshape(h, w) for i in range(3))
-        assert np.abs(q_class - O.guided_filter_class_run(g, s, r, eps)).max() <= TOL
+        q_chain = out[n * sch + 3 * n:].reshape(h, w, sch)
+        ref_class = O.guided_filter_class_run(g, s, r, eps)
+        assert np.abs(q_class - ref_class).max() <= TOL
         assert np.abs(q_fused - rq).max() <= TOL
-        if fill_ab:
+        # hBoxFilter / hMultiply / hCalcA / hCalcB / hLinearTransform chained as guided_filter.cpp:57-65 does
+        assert np.abs(q_chain - ref_class).max() <= TOL and np.abs(q_chain - q_class).max() <= 1e-5
+        if not skip_ab:
             assert np.abs(A - ra).max() <= TOL and np.abs(B - rb).max() <= TOL
 
 

@@ -122,8 +122,8 @@ def test_errors_are_loud(be):
 @pytest.mark.parametrize("border", [0, 1, 2])
 @pytest.mark.parametrize("shape,r", [((20, 64), 1), ((24, 100), 2), ((30, 40), 3), ((20, 520), 4), ((26, 36), 5),
                                      ((20, 48), 6), ((40, 133), 7), ((40, 600), 8), ((30, 64), 12), ((44, 500), 16)])
-def test_gray_fast(be, shape, r, border, monkeypatch):
-    monkeypatch.setenv("GF_DISABLE_S8", "1")
+def test_gray_fast(be, shape, r, border, knob):
+    knob(be, "GF_DISABLE_S8", 1)
     _gray_fast(be, shape, r, border)
 
 
@@ -138,8 +138,8 @@ def _gray_fast(be, shape, r, border):
     assert np.abs(q - ref).max() <= TOL
 
 
-def test_gray_fast_ab_batch_strip(be, monkeypatch):
-    monkeypatch.setenv("GF_DISABLE_S8", "1")
+def test_gray_fast_ab_batch_strip(be, knob):
+    knob(be, "GF_DISABLE_S8", 1)
     I, p = synth_pair(36, 64, seed=5)
     q, A, B = be.guided_gray(I, p, 4, 0.05, 0, want_ab=True)
     assert be.api.last_kernel() == "wp_r4"
@@ -162,8 +162,8 @@ def test_gray_fast_ab_batch_strip(be, monkeypatch):
         assert np.abs(qs - ref[y0:y1]).max() <= TOL
 
 
-def test_kat_crop_u8_fast(be, monkeypatch):
-    monkeypatch.setenv("GF_DISABLE_S8", "1")
+def test_kat_crop_u8_fast(be, knob):
+    knob(be, "GF_DISABLE_S8", 1)
     crop = [c for c in load_kat_crops() if c["name"] == "tl"][0]
     P, I = crop["P"][:60, :72], crop["I"][:60, :72]
     q = be.guided_gray(I, P, 7, 0.3, 0)
@@ -174,8 +174,8 @@ def test_kat_crop_u8_fast(be, monkeypatch):
 
 @pytest.mark.parametrize("shape,r,border", [((24, 1452), 4, 0), ((120, 400), 8, 1), ((90, 400), 7, 2), ((70, 360), 3, 0),
                                             ((60, 1100), 16, 0), ((90, 1500), 20, 0)])
-def test_gray_fast_steady_path(be, shape, r, border, monkeypatch):
-    monkeypatch.setenv("GF_DISABLE_S8", "1")
+def test_gray_fast_steady_path(be, shape, r, border, knob):
+    knob(be, "GF_DISABLE_S8", 1)
     """wide enough for a CTA strictly inside the image and tall enough for the straight-line
     steady-state loop (interior rows, 128-bit loads, constant normalisation) to run."""
     I, p = synth_pair(*shape, seed=51)
@@ -189,12 +189,12 @@ def test_gray_fast_steady_path(be, shape, r, border, monkeypatch):
                                             ((50, 264), 7, 0), ((70, 520), 7, 2), ((30, 300), 4, 0), ((40, 320), 4, 0), ((100, 640), 16, 0), ((140, 512), 32, 0),
                                             ((140, 456), 16, 2), ((75, 512), 8, 1), ((50, 264), 7, 1), ((100, 640), 16, 1),
                                             ((40, 320), 4, 1), ((180, 1000), 8, 1)])
-def test_gray_s8(be, shape, r, border, monkeypatch):
+def test_gray_s8(be, shape, r, border, knob):
     """interior and border strips (analytic edges, mirror loads, mapped loads, TRUNCATE counts),
     several bands (GF_S8_HB), a width that is not a multiple of 8 (partial last lane), heights that
     end inside / right after a re-seed period; the last case has warps that are interior in a
     TRUNCATE job (plain code) next to clipped ones."""
-    monkeypatch.setenv("GF_S8_HB", str(2 * r + 9))
+    knob(be, "GF_S8_HB", 2 * r + 9)
     I, p = synth_pair(*shape, seed=71, kind="structured")
     w = shape[1]
     q = be.guided_gray(I, p, r, 1e-2, border, pad=(-w) % 8)
@@ -203,10 +203,10 @@ def test_gray_s8(be, shape, r, border, monkeypatch):
 
 
 @pytest.mark.parametrize("shape,r,border", [((90, 1000), 8, 0), ((100, 960), 4, 0), ((120, 1000), 8, 1)])
-def test_gray_s8_two_band_classes(be, shape, r, border, monkeypatch):
+def test_gray_s8_two_band_classes(be, shape, r, border, knob):
     """the first and last strip in shorter bands than the interior strips (GF_S8_EDGE_PCT): item -> (strip, band) mapping"""
-    monkeypatch.setenv("GF_S8_HB", "40")
-    monkeypatch.setenv("GF_S8_EDGE_PCT", "65")
+    knob(be, "GF_S8_HB", 40)
+    knob(be, "GF_S8_EDGE_PCT", 65)
     I, p = synth_pair(*shape, seed=73, kind="structured")
     q = be.guided_gray(I, p, r, 1e-2, border)
     assert be.api.last_kernel() == f"s8_r{r}"
@@ -216,27 +216,27 @@ def test_gray_s8_two_band_classes(be, shape, r, border, monkeypatch):
 @pytest.mark.parametrize("shape,r,border,slots,pct", [((90, 1000), 8, 0, 1036, 85), ((90, 1000), 8, 0, 7, 85), ((90, 1000), 8, 0, 3, 60),
                                                       ((60, 704), 4, 1, 11, 85), ((75, 520), 7, 2, 5, 85), ((64, 256), 8, 0, 4, 85),
                                                       ((100, 640), 16, 0, 6, 70), ((41, 1000), 8, 0, 1, 85)])
-def test_gray_s8_tape(be, shape, r, border, slots, pct, monkeypatch):
+def test_gray_s8_tape(be, shape, r, border, slots, pct, knob):
     """tape scheduling (gf_tape_run): pieces shorter than a strip, pieces that cross strips, pieces that
     span several strips (few slots), weighted edge strips, one piece for the whole job.  (The uniform
     split differs in the last bits only: the running sums are re-seeded relative to the band start.)"""
-    monkeypatch.setenv("GF_TAPE", "1")
-    monkeypatch.setenv("GF_TAPE_SLOTS", str(slots))
-    monkeypatch.setenv("GF_S8_EDGE_PCT", str(pct))
+    knob(be, "GF_TAPE", 1)
+    knob(be, "GF_TAPE_SLOTS", slots)
+    knob(be, "GF_S8_EDGE_PCT", pct)
     I, p = synth_pair(*shape, seed=75, kind="structured")
     q = be.guided_gray(I, p, r, 1e-2, border)
     assert be.api.last_kernel() == f"s8_r{r}"
     assert np.abs(q - O.guided_filter_gray(I, p, r, 1e-2, border, np.float64)).max() <= TOL
-    monkeypatch.setenv("GF_TAPE", "0")
+    knob(be, "GF_TAPE", 0)
     q0 = be.guided_gray(I, p, r, 1e-2, border)
     assert np.abs(q - q0).max() <= 2e-6
 
 
-def test_tape_batch(be, monkeypatch):
+def test_tape_batch(be, knob):
     """pieces that cross from one frame into the next (gray and colour batches)"""
     rng = np.random.default_rng(18)
-    monkeypatch.setenv("GF_TAPE", "1")
-    monkeypatch.setenv("GF_TAPE_SLOTS", "5")
+    knob(be, "GF_TAPE", 1)
+    knob(be, "GF_TAPE_SLOTS", 5)
     Ib = rng.random((3, 40, 480), dtype=np.float32)
     pb = rng.random((3, 40, 480), dtype=np.float32)
     qb = be.batch(Ib, pb, 8, 1e-2, 0)
@@ -246,8 +246,8 @@ def test_tape_batch(be, monkeypatch):
     I = rng.random((3, 40, 160, 3), dtype=np.float32)
     p = rng.random((3, 40, 160), dtype=np.float32)
     for slots, we in ((5, 100), (2, 125)):
-        monkeypatch.setenv("GF_TAPE_SLOTS", str(slots))
-        monkeypatch.setenv("GF_C4_EDGE_WEIGHT", str(we))
+        knob(be, "GF_TAPE_SLOTS", slots)
+        knob(be, "GF_C4_EDGE_WEIGHT", we)
         q = be.batch(I, p, 8, 1e-2, 0)
         assert be.api.last_kernel() == "c4_r8"
         for k in range(3):
@@ -281,9 +281,9 @@ def test_gray_s8_batch_strip_kat(be):
 
 # ---- the tuned colour-guide kernel (gf_c4.cuh) under the emulator --------------------------------
 @pytest.mark.parametrize("shape,r", [((40, 160), 4), ((50, 256), 8), ((60, 132), 12), ((80, 192), 16)])
-def test_color_c4(be, shape, r, monkeypatch):
+def test_color_c4(be, shape, r, knob):
     """interior strips, border strips (mirror shuffles on both image edges), several bands."""
-    monkeypatch.setenv("GF_C4_HB", str(2 * r + 9))
+    knob(be, "GF_C4_HB", 2 * r + 9)
     h, w = shape
     rng = np.random.default_rng(40 + r)
     I3 = rng.random((h, w, 3), dtype=np.float32)
