@@ -110,7 +110,9 @@ def synth_frames(nsets):
 def cpu_port_bench(steps, warmup, budget_s, frames=None):
     """Times the C restatement of main.cpp:236-252 (oracle/libgf_oracle.so) on all host threads."""
     from oracle import c_oracle as C
-    nt = C.num_threads()
+    # Every core this process may run on -- NOT omp_get_max_threads(): torch.distributed.run exports
+    # OMP_NUM_THREADS=1 to its workers, which would shrink the CPU baseline to one thread at N > 1.
+    nt = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     I, p = frames if frames is not None else synth_frames(1)[0]
     t = time.perf_counter()
     C.guided_gray_f32(I, p, R, EPS, 0, nt)
@@ -307,6 +309,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     e2e_value = world * args.e2e_steps * PX / dt / 1e6
+    # the same call on PAGEABLE host memory (what the reference's caller holds: cv::Mat data, main.cpp:229-230)
+    pgI, pgP, pgQ = host[1][0].copy(), host[1][1].copy(), np.empty((H, W), np.float32)
+
+    def e2e_pageable_step():
+        api.call("gf_guided_gray_host", pgI.ctypes.data, pgP.ctypes.data, pgQ.ctypes.data, W, H, R, EPS, pkg.BORDER_REFLECT101)
+
+    for _ in range(2):
+        e2e_pageable_step()
+    barrier()
+    t0 = time.perf_counter()
+    npg = max(3, args.e2e_steps // 2)
+    for _ in range(npg):
+        e2e_pageable_step()
+    torch.cuda.synchronize()
+    dt_pg = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt_pg], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_pg = float(t.item())
+    e2e_pageable = {"value": world * npg * PX / dt_pg / 1e6, "unit": "Mpix/s", "ms_per_step": dt_pg / npg * 1e3, "steps": npg,
+                    "note": "same call, plain malloc'd (pageable) host buffers"}
     # the e2e result must be the right answer, not just fast
     step(0)
     torch.cuda.synchronize()
@@ -331,7 +354,7 @@ def main():
                      "algorithmic_bytes_per_px": ALG_BYTES_PER_PX},
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes,
                 "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3, "matches_device_path": e2e_ok,
-                "api": "gf_guided_gray_host (pinned host buffers)"},
+                "api": "gf_guided_gray_host (pinned host buffers)", "pageable": e2e_pageable},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -86,12 +86,27 @@ def main():
     jobs = [(e, c) for c in cases for e in envs] + extra
     if len(sys.argv) > 1 and sys.argv[1] == "--hb":
         jobs = [({"GF_WS": "1", "GF_WS_K": k, "GF_WS_HB": str(hb)}, (3840, 2160, 8)) for k in ("12", "8") for hb in (60, 84, 110, 167, 240, 360)]
+    if len(sys.argv) > 1 and sys.argv[1] == "--matrix":        # the default library: sizes x K, borders, radii, old kernel beside it
+        ws = lambda k: {"GF_WS": "1", "GF_WS_K": str(k)}
+        jobs = [(e, c) for c in ((3840, 2160, 8), (7680, 4320, 8), (1920, 1080, 8), (16384, 8192, 8)) for e in (ws(12), ws(8), {"GF_WS": "0"})]
+        jobs += [(ws(12), (3840, 2160, 8, 1)), (ws(12), (3840, 2160, 8, 2)), (ws(12), (3840, 2160, 16)), (ws(8), (3840, 2160, 16)),
+                 ({"GF_WS": "0"}, (3840, 2160, 16)), (ws(12), (3840, 2160, 7)), (ws(8), (3840, 2160, 4)), ({"GF_WS": "0"}, (3840, 2160, 4))]
+    if len(sys.argv) > 1 and sys.argv[1] == "--split":         # producer split on / off, edge band weight
+        jobs = []
+        for c in ((3840, 2160, 8), (7680, 4320, 8), (1920, 1080, 8), (16384, 8192, 8)):
+            for k in (12, 8):
+                for sp in (0, 1):
+                    jobs.append(({"GF_WS": "1", "GF_WS_K": str(k), "GF_WS_SPLIT1": str(sp)}, c))
+        for pct in (100, 120, 150):
+            jobs.append(({"GF_WS": "1", "GF_WS_K": "12", "GF_WS_SPLIT1": "1", "GF_WS_EDGE_PCT": str(pct)}, (3840, 2160, 8)))
+        jobs += [({"GF_WS": "1", "GF_WS_SPLIT1": "1"}, (3840, 2160, 16)), ({"GF_WS": "1", "GF_WS_SPLIT1": "1", "GF_WS_K": "8"}, (3840, 2160, 16)),
+                 ({"GF_WS": "1", "GF_WS_SPLIT1": "1"}, (3840, 2160, 4)), ({"GF_WS": "1", "GF_WS_SPLIT1": "1"}, (3840, 2160, 8, 1))]
     if len(sys.argv) > 1 and sys.argv[1] == "--variants":      # differently compiled builds: ws_bench.py --variants libA.so libB.so ...
         libs = sys.argv[2:]
         jobs = []
         for lib in libs:
             path = os.path.join(ROOT, "cudaimageprocessing_b200", lib)
-            for k in ("12", "8"):
+            for k in ("12",):
                 for c in ((3840, 2160, 8), (7680, 4320, 8)):
                     jobs.append(({"GF_LIB_PATH": path, "GF_WS": "1", "GF_WS_K": k}, c))
     for env, c in jobs:

@@ -23,6 +23,13 @@ SIGNATURES = {
                                 c_int, c_float, c_int, P]),
     "gf_guided_gray_strip": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64,
                                      c_int, c_float, c_int, P]),
+    "gf_strip_layout": (c_int, [c_int, c_int, c_int, c_int, P, P]),
+    "gf_run_strips": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_float, c_int, P, P, P]),
+    "gf_device_alloc": (c_int, [P, c_size_t]),
+    "gf_device_free": (c_int, [P]),
+    "gf_ipc_export": (c_int, [P, P]),
+    "gf_ipc_open": (c_int, [P, P]),
+    "gf_ipc_close": (c_int, [P]),
     "gf_box_filter": (c_int, [P, P, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int, P]),
     "gf_multiply": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, P]),
     "gf_calc_a": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_float, P]),
@@ -40,6 +47,11 @@ SIGNATURES = {
     "gf_launch_count": (c_int64, []),
     "gf_set_option": (c_int, [ctypes.c_char_p, c_int]),
 }
+
+
+class StripPeer(ctypes.Structure):
+    """gf_strip_peer (include/gf_b200.h): a neighbour's strip buffers as seen from this device."""
+    _fields_ = [("guide", P), ("src", P), ("guide_stride", c_int64), ("src_stride", c_int64), ("top", c_int), ("rows", c_int)]
 
 
 class GfError(RuntimeError):

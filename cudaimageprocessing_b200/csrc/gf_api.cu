@@ -524,6 +524,131 @@ int gf_guided_gray_strip(const float* guide, const float* src, float* dst, int w
     return run_jobs(&j, 1);
 }
 
+// ---- row strips with the halo exchange inside the call (gf_run_strips) ------------------------
+static void strip_halo_rows(int global_height, int y0, int rows, int r, int* top, int* bot)
+{
+    *top = y0 > 0 ? (2 * r < y0 ? 2 * r : y0) : 0;
+    const int below = global_height - (y0 + rows);
+    *bot = below > 0 ? (2 * r < below ? 2 * r : below) : 0;
+}
+
+int gf_strip_layout(int global_height, int y0, int rows, int r, int* top, int* bot)
+{
+    if (!top || !bot) return fail(GF_ERR_INVALID, "gf_strip_layout: null pointer");
+    if (global_height <= 0 || y0 < 0 || rows <= 0 || y0 + rows > global_height || r < 0) return fail(GF_ERR_INVALID, "gf_strip_layout: rows outside the image");
+    strip_halo_rows(global_height, y0, rows, r, top, bot);
+    return GF_OK;
+}
+
+int gf_run_strips(float* guide_buf, float* src_buf, float* dst, int width, int global_height, int y0, int rows, int64_t guide_stride,
+                  int64_t src_stride, int64_t dst_stride, int r, float eps, int border, const gf_strip_peer* up, const gf_strip_peer* down,
+                  void* stream)
+{
+    if (!guide_buf || !src_buf || !dst) return fail(GF_ERR_INVALID, "gf_run_strips: null image pointer");
+    if (width <= 0 || global_height <= 0 || y0 < 0 || rows <= 0 || y0 + rows > global_height || r < 0)
+        return fail(GF_ERR_INVALID, "gf_run_strips: strip [%d,%d) outside the %d-row image", y0, y0 + rows, global_height);
+    int top = 0, bot = 0;
+    strip_halo_rows(global_height, y0, rows, r, &top, &bot);
+    const int64_t gs = or_packed(guide_stride, width, 1), ss = or_packed(src_stride, width, 1);
+    // every neighbour must be able to supply the halo from its OWN rows (checked identically on every rank:
+    // the numbers come from the geometry, not from what a neighbour says about itself)
+    if ((up && top > 0 && up->rows < top) || (down && bot > 0 && down->rows < bot))
+        return fail(GF_ERR_INVALID, "gf_run_strips: a neighbour strip is shorter than the %d-row halo it must supply", 2 * r);
+#ifndef GF_CPU_EMU
+    const size_t row_bytes = (size_t)width * sizeof(float);
+    auto pull = [&](float* dst_rows, int64_t dstride, const float* peer, int64_t pstride, int first_row, int n) -> cudaError_t {
+        if (n <= 0) return cudaSuccess;
+        const int64_t ps = pstride > 0 ? pstride : width;
+        return cudaMemcpy2DAsync(dst_rows, (size_t)dstride * sizeof(float), peer + (int64_t)first_row * ps, (size_t)ps * sizeof(float),
+                                 row_bytes, (size_t)n, cudaMemcpyDefault, (cudaStream_t)stream);
+    };
+    cudaError_t e = cudaSuccess;
+    if (up && top > 0) {           // the LAST `top` own rows of the strip above -> my first `top` rows
+        if (!up->guide || !up->src) return fail(GF_ERR_INVALID, "gf_run_strips: null peer pointer (up)");
+        const int first = up->top + up->rows - top;
+        if ((e = pull(guide_buf, gs, up->guide, up->guide_stride, first, top)) == cudaSuccess) e = pull(src_buf, ss, up->src, up->src_stride, first, top);
+    }
+    if (e == cudaSuccess && down && bot > 0) {    // the FIRST `bot` own rows of the strip below -> my last `bot` rows
+        if (!down->guide || !down->src) return fail(GF_ERR_INVALID, "gf_run_strips: null peer pointer (down)");
+        const int64_t off = (int64_t)(top + rows);
+        if ((e = pull(guide_buf + off * gs, gs, down->guide, down->guide_stride, down->top, bot)) == cudaSuccess)
+            e = pull(src_buf + off * ss, ss, down->src, down->src_stride, down->top, bot);
+    }
+    if (e != cudaSuccess) return fail(GF_ERR_CUDA, "gf_run_strips: peer copy of the halo rows: %s", cudaGetErrorString(e));
+#else
+    auto pull = [&](float* dst_rows, int64_t dstride, const float* peer, int64_t pstride, int first_row, int n) {
+        const int64_t ps = pstride > 0 ? pstride : width;
+        for (int y = 0; y < n; ++y) std::memcpy(dst_rows + y * dstride, peer + (int64_t)(first_row + y) * ps, (size_t)width * sizeof(float));
+    };
+    if (up && top > 0) { const int first = up->top + up->rows - top; pull(guide_buf, gs, up->guide, up->guide_stride, first, top); pull(src_buf, ss, up->src, up->src_stride, first, top); }
+    if (down && bot > 0) { const int64_t off = (int64_t)(top + rows); pull(guide_buf + off * gs, gs, down->guide, down->guide_stride, down->top, bot); pull(src_buf + off * ss, ss, down->src, down->src_stride, down->top, bot); }
+#endif
+    return gf_guided_gray_strip(guide_buf, src_buf, dst, width, global_height, y0 - top, top + rows + bot, y0, rows, gs, ss, dst_stride, r, eps,
+                                border, stream);
+}
+
+// device allocations that can be shared with the other ranks of a node (CUDA IPC needs allocation base pointers)
+int gf_device_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) return fail(GF_ERR_INVALID, "null pointer");
+#ifdef GF_CPU_EMU
+    *ptr = std::aligned_alloc(256, (bytes + 255) / 256 * 256);
+    return *ptr ? GF_OK : fail(GF_ERR_NOMEM, "malloc");
+#else
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    return e == cudaSuccess ? GF_OK : fail(GF_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+#endif
+}
+
+int gf_device_free(void* ptr)
+{
+#ifdef GF_CPU_EMU
+    std::free(ptr);
+    return GF_OK;
+#else
+    cudaError_t e = cudaFree(ptr);
+    return e == cudaSuccess ? GF_OK : fail(GF_ERR_CUDA, "cudaFree: %s", cudaGetErrorString(e));
+#endif
+}
+
+int gf_ipc_export(const void* ptr, void* handle64)
+{
+    if (!ptr || !handle64) return fail(GF_ERR_INVALID, "null pointer");
+#ifdef GF_CPU_EMU
+    return fail(GF_ERR_UNSUPPORTED, "no IPC in the emulator build");
+#else
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(ptr));
+    if (e != cudaSuccess) return fail(GF_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    std::memcpy(handle64, &h, 64);
+    return GF_OK;
+#endif
+}
+
+int gf_ipc_open(const void* handle64, void** ptr)
+{
+    if (!ptr || !handle64) return fail(GF_ERR_INVALID, "null pointer");
+#ifdef GF_CPU_EMU
+    return fail(GF_ERR_UNSUPPORTED, "no IPC in the emulator build");
+#else
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? GF_OK : fail(GF_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+#endif
+}
+
+int gf_ipc_close(void* ptr)
+{
+#ifdef GF_CPU_EMU
+    return GF_OK;
+#else
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    return e == cudaSuccess ? GF_OK : fail(GF_ERR_CUDA, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e));
+#endif
+}
+
 int gf_box_filter(const float* src, float* dst, int width, int height, int channels, int64_t src_stride, int64_t dst_stride,
                   int r, int border, void* stream)
 {

@@ -17,6 +17,9 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
 #else
 namespace {
 const int kMaxBands = 16;
+const int kMaxDevices = 64;
+// One pipe per DEVICE (streams, events and the staging planes live on it), each with its own lock: callers on
+// different GPUs never serialise, callers on the same GPU share its staging planes and take turns.
 struct HostPipe {
     std::mutex mu;
     float* dev = nullptr;      // guide | src | dst planes
@@ -24,15 +27,27 @@ struct HostPipe {
     cudaStream_t up = nullptr, comp = nullptr, down = nullptr;
     cudaEvent_t ev_up[kMaxBands], ev_k[kMaxBands];
     bool init = false;
-    int device = -1;
 };
-HostPipe g_pipe;
+HostPipe g_pipes[kMaxDevices];
 
 #define GF_CU(call)                                                                  \
     do {                                                                             \
         cudaError_t e_ = (call);                                                     \
         if (e_ != cudaSuccess) return fail(GF_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
+// inside the band loop: copies touching the caller's buffers may be in flight -> drain the pipe before returning
+#define GF_CU_DRAIN(call)                                                            \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) { drain(P); return fail(GF_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+
+void drain(HostPipe& P)
+{
+    cudaStreamSynchronize(P.up);
+    cudaStreamSynchronize(P.comp);
+    cudaStreamSynchronize(P.down);
+}
 }  // namespace
 
 extern "C" {
@@ -54,11 +69,12 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
 {
     if (!guide || !src || !dst) return fail(GF_ERR_INVALID, "null image pointer");
     if (width <= 0 || height <= 0 || r < 0) return fail(GF_ERR_INVALID, "bad geometry %dx%d r=%d", width, height, r);
-    HostPipe& P = g_pipe;
-    std::lock_guard<std::mutex> lock(P.mu);
     int dev = 0;
     GF_CU(cudaGetDevice(&dev));
-    if (!P.init || P.device != dev) {
+    if (dev < 0 || dev >= kMaxDevices) return fail(GF_ERR_UNSUPPORTED, "device index %d", dev);
+    HostPipe& P = g_pipes[dev];
+    std::lock_guard<std::mutex> lock(P.mu);
+    if (!P.init) {
         GF_CU(cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
         GF_CU(cudaStreamCreateWithFlags(&P.comp, cudaStreamNonBlocking));
         GF_CU(cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
@@ -67,16 +83,14 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
             GF_CU(cudaEventCreateWithFlags(&P.ev_k[i], cudaEventDisableTiming));
         }
         P.init = true;
-        P.device = dev;
-        P.dev = nullptr;
-        P.cap = 0;
     }
     const size_t n = (size_t)width * height;
-    if (n > P.cap) {
+    if (n > P.cap) {               // grow-only staging planes; nothing is in flight here (every call drains before it returns)
         if (P.dev) GF_CU(cudaFree(P.dev));
         P.dev = nullptr;
         P.cap = 0;
-        GF_CU(cudaMalloc((void**)&P.dev, 3 * n * sizeof(float)));
+        cudaError_t e = cudaMalloc((void**)&P.dev, 3 * n * sizeof(float));
+        if (e != cudaSuccess) { P.dev = nullptr; return fail(GF_ERR_NOMEM, "staging planes (%zu bytes): %s", 3 * n * sizeof(float), cudaGetErrorString(e)); }
         P.cap = n;
     }
     float *dI = P.dev, *dP = P.dev + P.cap, *dQ = P.dev + 2 * P.cap;
@@ -92,19 +106,19 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
         if (need > height || b == nb - 1) need = height;
         if (need > up_to) {
             const size_t off = (size_t)up_to * width, cnt = (size_t)(need - up_to) * width * sizeof(float);
-            GF_CU(cudaMemcpyAsync(dI + off, guide + off, cnt, cudaMemcpyHostToDevice, P.up));
-            GF_CU(cudaMemcpyAsync(dP + off, src + off, cnt, cudaMemcpyHostToDevice, P.up));
+            GF_CU_DRAIN(cudaMemcpyAsync(dI + off, guide + off, cnt, cudaMemcpyHostToDevice, P.up));
+            GF_CU_DRAIN(cudaMemcpyAsync(dP + off, src + off, cnt, cudaMemcpyHostToDevice, P.up));
             up_to = need;
         }
-        GF_CU(cudaEventRecord(P.ev_up[b], P.up));
-        GF_CU(cudaStreamWaitEvent(P.comp, P.ev_up[b], 0));
+        GF_CU_DRAIN(cudaEventRecord(P.ev_up[b], P.up));
+        GF_CU_DRAIN(cudaStreamWaitEvent(P.comp, P.ev_up[b], 0));
         // rows [0, up_to) are resident; the band reads at most rows [y0-2r, y1+2r) after mapping
         int rc = gf_guided_gray_strip(dI, dP, dQ + (size_t)y0 * width, width, height, 0, up_to, y0, y1 - y0, width, width, width,
                                       r, eps, border, P.comp);
-        if (rc) return rc;
-        GF_CU(cudaEventRecord(P.ev_k[b], P.comp));
-        GF_CU(cudaStreamWaitEvent(P.down, P.ev_k[b], 0));
-        GF_CU(cudaMemcpyAsync(dst + (size_t)y0 * width, dQ + (size_t)y0 * width, (size_t)(y1 - y0) * width * sizeof(float),
+        if (rc) { drain(P); return rc; }
+        GF_CU_DRAIN(cudaEventRecord(P.ev_k[b], P.comp));
+        GF_CU_DRAIN(cudaStreamWaitEvent(P.down, P.ev_k[b], 0));
+        GF_CU_DRAIN(cudaMemcpyAsync(dst + (size_t)y0 * width, dQ + (size_t)y0 * width, (size_t)(y1 - y0) * width * sizeof(float),
                               cudaMemcpyDeviceToHost, P.down));
     }
     GF_CU(cudaStreamSynchronize(P.down));

@@ -34,6 +34,12 @@
 #ifndef GF_WS_NEWTON
 #define GF_WS_NEWTON 1       // one Newton step after MUFU.RCP in the a/b solve
 #endif
+#ifndef GF_WS_SPLIT
+#define GF_WS_SPLIT 1        // prefix / suffix chains of the window sums in two halves
+#endif
+#ifndef GF_WS_PF
+#define GF_WS_PF 6           // rows ahead for the L2 prefetch hint of the entering row (0 = off)
+#endif
 #ifndef GF_WS_NORM2
 #define GF_WS_NORM2 1        // two-term reciprocal of the pixel count (see GfNorm)
 #endif
@@ -44,6 +50,7 @@ struct GfWsArgs {
     int64_t gfs, sfs, dfs, abfs;     // frame strides
     int width, height, buf_y0, buf_rows, out_y0, out_rows, border;
     int nstrips, nbands, hb, count;
+    int nbands_e, hb_e;              // band count / height of the first and last strip (0: same as the others)
     float eps;
 };
 
@@ -58,7 +65,8 @@ struct GfWsGeom {
     static constexpr int RING = 2 * R + 2;               // a/b rows per stream
     static constexpr int ROW_F4 = (K / 2) * 32;          // float4 per ring row: [pair of columns][lane] = (a0, b0, a1, b1)
     static constexpr size_t ring_bytes = (size_t)RING * ROW_F4 * 16;
-    static constexpr size_t ctrl_bytes = 64 + (size_t)NS * RING * 8;      // 2 NS row counters + one mbarrier per ring slot
+    static constexpr int NBAR = 2 * RING + 1;            // mbarriers per stream: row ready + products ready per ring slot, "stream finished"
+    static constexpr size_t ctrl_bytes = 64 + (size_t)NS * NBAR * 8;      // 2 NS row counters + the mbarriers
     static constexpr size_t smem_bytes = (size_t)NS * ring_bytes + (ctrl_bytes + 127) / 128 * 128;
     static constexpr int MIN_SUB = R + 1;                // shortest sub-band whose neighbours can share rows with it
 };
@@ -142,11 +150,16 @@ __device__ __forceinline__ void gf_ws_row_ready(volatile int* prod, unsigned lon
     gf_ws_publish(prod, idx + 1, lane);
 #endif
 }
+// `last_rows`: the row is one of the LAST rows of another stream (the neighbour across a shared end).  A slot
+// barrier only tells phase p from p-1 (one parity bit): a consumer that arrives while that producer is still more
+// than a ring behind would take the completion of phase p-1 for phase p.  Those rows wait for the producer's
+// "stream finished" barrier instead (its last row is the first one needed anyway).
 template <int RING>
-__device__ __forceinline__ void gf_ws_row_wait(const volatile int* prod, const unsigned long long* bars, int idx)
+__device__ __forceinline__ void gf_ws_row_wait(const volatile int* prod, const unsigned long long* bars, int idx, bool last_rows)
 {
 #if GF_WS_SYNC == 2
-    gf_ws_bar_wait(bars + idx % RING, idx / RING);
+    if (last_rows) gf_ws_bar_wait(bars + 2 * RING, 0);
+    else gf_ws_bar_wait(bars + idx % RING, idx / RING);
 #else
     gf_ws_wait(prod, idx + 1);
 #endif
@@ -171,12 +184,30 @@ template <int K, int R>
 __device__ __forceinline__ void gf_ws_window(const float2 (&v)[K], float2 (&w)[K])
 {
     float2 P[K], S[K];
+#if GF_WS_SPLIT
+    // two half-length chains per direction instead of one (dependency depth K/2 + 1 instead of K - 1; K/2 more
+    // additions): a lone producer warp per scheduler otherwise waits on FADD2 latency at every step
+    constexpr int HF = K / 2;
+    P[0] = v[0];
+    P[HF] = v[HF];
+#pragma unroll
+    for (int j = 1; j < HF; ++j) { P[j] = gf_add2(P[j - 1], v[j]); P[HF + j] = gf_add2(P[HF + j - 1], v[HF + j]); }
+#pragma unroll
+    for (int j = HF; j < K; ++j) P[j] = gf_add2(P[j], P[HF - 1]);
+    S[K - 1] = v[K - 1];
+    S[HF - 1] = v[HF - 1];
+#pragma unroll
+    for (int j = 1; j < HF; ++j) { S[K - 1 - j] = gf_add2(S[K - j], v[K - 1 - j]); S[HF - 1 - j] = gf_add2(S[HF - j], v[HF - 1 - j]); }
+#pragma unroll
+    for (int j = 0; j < HF; ++j) S[j] = gf_add2(S[j], S[HF]);
+#else
     P[0] = v[0];
 #pragma unroll
     for (int j = 1; j < K; ++j) P[j] = gf_add2(P[j - 1], v[j]);
     S[K - 1] = v[K - 1];
 #pragma unroll
     for (int j = K - 2; j >= 0; --j) S[j] = gf_add2(S[j + 1], v[j]);
+#endif
     constexpr int CM = (R + K - 1) / K;      // farthest lane a window reaches
     // cumulative totals of the c nearest lanes on either side (only when R > K)
     float2 TL[CM + 1], TR[CM + 1];
@@ -202,6 +233,27 @@ __device__ __forceinline__ void gf_ws_window(const float2 (&v)[K], float2 (&w)[K
         }
         w[j] = acc;
     }
+}
+
+// ---- image edges of the first / last strip: mirror the COLUMN SUMS, not the loads ----------------------
+// A column outside the image carries the sums of the in-image column it mirrors (REFLECT101: u' = C - u in strip
+// coordinates, REFLECT: the same with C shifted by one), so instead of gathering mirrored pixels for every loaded
+// row the producer copies the four vertical sums across lanes once per row: for source register js the target
+// register is (C - js) mod K and the source lane is q - lane, both compile-time per js.  K shuffles per
+// component, only in the two edge strips.  TRUNCATE: the outside columns are simply zero.
+template <int K, int C>
+__device__ __forceinline__ void gf_ws_mirror(float2 (&v)[K], int lane, unsigned oob)
+{
+    float2 t[K];
+#pragma unroll
+    for (int js = 0; js < K; ++js) {
+        const int j = ((C - js) % K + K) % K;            // target register fed by source register js
+        const int q = (C - j - js) / K;                  // source lane = q - lane
+        t[j] = make_float2(__shfl_sync(0xffffffffu, v[js].x, (q - lane) & 31), __shfl_sync(0xffffffffu, v[js].y, (q - lane) & 31));
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if (oob >> j & 1) v[j] = t[j];
 }
 
 // ---- sub-band plan of one CTA ----------------------------------------------------------------------
@@ -257,7 +309,13 @@ __host__ __device__ inline void gf_ws_plan(int y0, int y1, GfWsPlan<NS>& pl)
 }
 
 // ---- stage 1: producer warp -------------------------------------------------------------------------
-template <int R, int K, int NS, bool TRUNC, bool EDGE>
+// EM: 0 the strip window lies inside the image, 1 it overhangs the left edge by exactly HALO columns, 2 the right
+// edge by exactly HALO (the last strip is placed that way), 3 anything else: per-column map + gathered loads.
+// ROLE: 0 one producer warp per stream; 1 / 2 the producer split over TWO warps (3 warps per scheduler instead of 2,
+// each with half the dependent chain): warp 2 owns Y = (sum Ip, sum II), its window sums go into the ring slot of the
+// row (the slot is free by then); warp 1 owns X = (sum I, sum p), picks the Y sums up from the slot, solves for a, b
+// and overwrites the slot with them.
+template <int R, int K, int NS, bool TRUNC, int EM, int ROLE>
 __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<NS>& pl, int k, int lane, int64_t f, int xl,
                                              int out_lo, int out_hi, float4* rings, volatile int* ctrl)
 {
@@ -266,12 +324,20 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
     const GfWsStream st = pl.s[k];
     float4* ring = rings + (size_t)k * RING * G::ROW_F4 + lane;
     const int x0 = xl + lane * K;
-    // EDGE = false: every column of the strip's window lies inside the image (no column map in the code at all)
+    constexpr bool EDGE = EM == 3;
     const bool vec = !EDGE || (x0 >= 0 && x0 + K <= a.width);
     int sx[EDGE ? K : 1];
     if (EDGE) {
 #pragma unroll
         for (int j = 0; j < K; ++j) sx[j] = gf_map(x0 + j, a.width, a.border);
+    }
+    unsigned oob = 0, cmask = ~0u;            // EM 1, 2: columns outside the image / 4-column groups that may be loaded
+    if (EM == 1 || EM == 2) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) oob |= (x0 + j < 0 || x0 + j >= a.width) ? 1u << j : 0u;
+#pragma unroll
+        for (int c = 0; c < K / 4; ++c)
+            if (x0 + 4 * c < 0 || x0 + 4 * c + 4 > a.width) cmask &= ~(1u << c);
     }
     const float* gI = a.guide + f * a.gfs;            // column 0 (the column map of EDGE lanes is absolute)
     const float* gP = a.src + f * a.sfs;
@@ -280,13 +346,32 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
     const int rows_hi = (a.buf_y0 + a.buf_rows < a.height ? a.buf_y0 + a.buf_rows : a.height) - 1 - a.buf_y0;
 
     // buffer row of stream-local input row t, -1 = a row of zeros (TRUNCATE outside the image)
+    // (streams whose whole input range [m0-R, m1+R] lies inside the image and the buffer skip the border map)
+    const int t_first = st.m0 - R, t_last = st.m1 + R;
+    const int ya = st.ys + st.d * t_first, yb = st.ys + st.d * t_last;
+    const bool simple = (ya < yb ? ya : yb) >= a.buf_y0 && (ya > yb ? ya : yb) <= a.buf_y0 + rows_hi;
+    const int rbase = st.ys - a.buf_y0;
     auto row_of = [&](int t) -> int {
+        if (simple) return rbase + st.d * t;
         int y = st.ys + st.d * t;
         if (TRUNC) { if (y < 0 || y >= a.height) return -1; }
         else y = gf_s8_map_y(y, a.height, a.border);
         int rr = y - a.buf_y0;
         rr = rr < 0 ? 0 : (rr > rows_hi ? rows_hi : rr);
         return rr;
+    };
+    // L2 prefetch hint for the row that enters GF_WS_PF iterations from now: one 128-byte line per lane and plane
+    auto prefetch_row = [&](int t) {
+        if (GF_WS_PF == 0 || EM == 3) return;
+        if (lane * 32 < G::WIN) {
+            int rr = row_of(t);
+            if (!simple) { if (TRUNC && rr < 0) return; }
+            const int64_t c0 = (int64_t)xl + lane * 32;
+            if (c0 >= 0 && c0 + 32 <= a.width) {
+                gf_prefetch_l2(gI + (int64_t)rr * a.gs + c0);
+                gf_prefetch_l2(gP + (int64_t)rr * a.ss + c0);
+            }
+        }
     };
     auto ld_row = [&](const float* plane, const float* planex, int64_t stride, int rr, float (&v)[K]) {
         if (TRUNC && rr < 0) {
@@ -297,7 +382,14 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
         const int64_t ro = (int64_t)rr * stride;
         if (vec) {
             const float* rp = planex + ro;
-            if (K % 8 == 0) {              // one 32-byte access per 8 columns: lane stride = access size, fully coalesced
+            if (EM == 1 || EM == 2) {      // edge strip: groups outside the image are not read (their sums are mirrored in)
+#pragma unroll
+                for (int c = 0; c < K / 4; ++c) {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cmask >> c & 1) t = *reinterpret_cast<const float4*>(rp + 4 * c);
+                    v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+                }
+            } else if (K % 8 == 0) {       // one 32-byte access per 8 columns: lane stride = access size, fully coalesced
 #pragma unroll
                 for (int c = 0; c < K / 8; ++c) {
                     float2 t[4];
@@ -342,9 +434,11 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
                 if (t0 + q >= t_end) break;
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    X[j].x += bI[q][j]; X[j].y += bP[q][j];
-                    Y[j].x = fmaf(bI[q][j], bP[q][j], Y[j].x);
-                    Y[j].y = fmaf(bI[q][j], bI[q][j], Y[j].y);
+                    if (ROLE != 2) { X[j].x += bI[q][j]; X[j].y += bP[q][j]; }
+                    if (ROLE != 1) {
+                        Y[j].x = fmaf(bI[q][j], bP[q][j], Y[j].x);
+                        Y[j].y = fmaf(bI[q][j], bI[q][j], Y[j].y);
+                    }
                 }
             }
         }
@@ -377,19 +471,41 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
 #pragma unroll 1
     for (int m = st.m0; m < st.m1; ++m) {
         // ---- vertical: row m+R enters, row m-R-1 leaves ----
+        if (ROLE != 2) {
 #pragma unroll
-        for (int c = 0; c < K / 2; ++c) {      // (entering - leaving) on the column pairs the loads deliver: FADD2
-            const float2 dI = gf_sub2(make_float2(nI[2 * c], nI[2 * c + 1]), make_float2(oI[2 * c], oI[2 * c + 1]));
-            const float2 dP = gf_sub2(make_float2(nP[2 * c], nP[2 * c + 1]), make_float2(oP[2 * c], oP[2 * c + 1]));
-            X[2 * c].x += dI.x; X[2 * c + 1].x += dI.y;
-            X[2 * c].y += dP.x; X[2 * c + 1].y += dP.y;
+            for (int c = 0; c < K / 2; ++c) {      // (entering - leaving) on the column pairs the loads deliver: FADD2
+                const float2 dI = gf_sub2(make_float2(nI[2 * c], nI[2 * c + 1]), make_float2(oI[2 * c], oI[2 * c + 1]));
+                const float2 dP = gf_sub2(make_float2(nP[2 * c], nP[2 * c + 1]), make_float2(oP[2 * c], oP[2 * c + 1]));
+                X[2 * c].x += dI.x; X[2 * c + 1].x += dI.y;
+                X[2 * c].y += dP.x; X[2 * c + 1].y += dP.y;
+            }
         }
+        if (ROLE != 1) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            Y[j].x = fmaf(-oI[j], oP[j], fmaf(nI[j], nP[j], Y[j].x));
-            Y[j].y = fmaf(-oI[j], oI[j], fmaf(nI[j], nI[j], Y[j].y));
+            for (int j = 0; j < K; ++j) {
+                Y[j].x = fmaf(-oI[j], oP[j], fmaf(nI[j], nP[j], Y[j].x));
+                Y[j].y = fmaf(-oI[j], oI[j], fmaf(nI[j], nI[j], Y[j].y));
+            }
+        }
+        if (EM == 1 || EM == 2) {
+            if (TRUNC) {
+#pragma unroll
+                for (int j = 0; j < K; ++j)
+                    if (oob >> j & 1) X[j] = Y[j] = make_float2(0.f, 0.f);
+            } else {
+                constexpr int CL0 = 2 * G::HALO, CR0 = 2 * (G::WIN - G::HALO - 1);
+                if (a.border == GF_REFLECT) {
+                    if (EM == 1) { if (ROLE != 2) gf_ws_mirror<K, CL0 - 1>(X, lane, oob); if (ROLE != 1) gf_ws_mirror<K, CL0 - 1>(Y, lane, oob); }
+                    else { if (ROLE != 2) gf_ws_mirror<K, CR0 + 1>(X, lane, oob); if (ROLE != 1) gf_ws_mirror<K, CR0 + 1>(Y, lane, oob); }
+                } else {
+                    if (EM == 1) { if (ROLE != 2) gf_ws_mirror<K, CL0>(X, lane, oob); if (ROLE != 1) gf_ws_mirror<K, CL0>(Y, lane, oob); }
+                    else { if (ROLE != 2) gf_ws_mirror<K, CR0>(X, lane, oob); if (ROLE != 1) gf_ws_mirror<K, CR0>(Y, lane, oob); }
+                }
+            }
         }
         // ---- rows of the next iteration (a whole iteration to land) ----
+        if (ROLE != 1 && m + GF_WS_PF + 1 < st.m1) prefetch_row(m + 1 + R + GF_WS_PF);
+        const int cons_seen = ROLE != 1 ? gf_ws_ld_acq(cons_own) : 0;      // read early, needed just before the ring store
         if (m + 1 < st.m1) {
             const int rn = row_of(m + 1 + R), ro = row_of(m - R);
             ld_row(gI, gIx, a.gs, rn, nI);
@@ -398,9 +514,38 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
             ld_row(gP, gPx, a.ss, ro, oP);
         }
         // ---- horizontal: window sums of the two quantity pairs ----
+        const int idx = m - st.m0;
         float2 hX[K], hY[K];
-        gf_ws_window<K, R>(X, hX);
-        gf_ws_window<K, R>(Y, hY);
+        if (ROLE != 2) gf_ws_window<K, R>(X, hX);
+        if (ROLE != 1) gf_ws_window<K, R>(Y, hY);
+        if (ROLE == 2) {
+            // products warp: wait until every consumer is done with the row the slot held, park the Y sums in it
+            if (idx >= RING) {
+                const int mm = m - RING;
+                const int use = mm + KW < n_last ? mm + KW : n_last;
+                if (cons_seen < use + R + 1) gf_ws_wait(cons_own, use + R + 1);
+                if (st.sp >= 0 && mm < R) {
+                    const int usep = 2 * R - mm < n_last_sp ? 2 * R - mm : n_last_sp;
+                    gf_ws_wait(cons_sp, usep + R + 1);
+                }
+            }
+            float4* rp = ring + slot * G::ROW_F4;
+#pragma unroll
+            for (int c = 0; c < K / 2; ++c) rp[c * 32] = make_float4(hY[2 * c].x, hY[2 * c].y, hY[2 * c + 1].x, hY[2 * c + 1].y);
+            __syncwarp();
+            if (lane == 0) gf_ws_bar_arrive(bars + k * G::NBAR + RING + slot);
+            slot = slot + 1 == RING ? 0 : slot + 1;
+            continue;
+        }
+        if (ROLE == 1) {
+            gf_ws_bar_wait(bars + k * G::NBAR + RING + slot, idx / RING);
+            const float4* rp = ring + slot * G::ROW_F4;
+#pragma unroll
+            for (int c = 0; c < K / 2; ++c) {
+                const float4 t = rp[c * 32];
+                hY[2 * c] = make_float2(t.x, t.y); hY[2 * c + 1] = make_float2(t.z, t.w);
+            }
+        }
         // ---- a = (N S_Ip - S_I S_p) / (N S_II - S_I^2 + eps N^2),  bN = S_p - a S_I  (b = bN / N) ----
         float av[K], bv[K];
         if (TRUNC) {
@@ -418,7 +563,7 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
                 rn = fmaf(fmaf(-n2, rn, 1.0f), rn, rn);
                 const float aa = num * rc;
                 const float bb = fmaf(-aa, hX[j].x, hX[j].y) * rn;
-                const bool ok = rowin && (!EDGE || sx[j] >= 0);
+                const bool ok = rowin && (EDGE ? sx[j] >= 0 : !(oob >> j & 1));
                 av[j] = ok ? aa : 0.f;
                 bv[j] = ok ? bb : 0.f;
             }
@@ -437,11 +582,10 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
             }
         }
         // ---- the ring slot of row m held row m-RING: every consumer of that row must be done with it ----
-        const int idx = m - st.m0;
-        if (idx >= RING) {
+        if (ROLE == 0 && idx >= RING) {
             const int mm = m - RING;
             const int use = mm + KW < n_last ? mm + KW : n_last;          // last step of the own consumer that reads row mm
-            gf_ws_wait(cons_own, use + R + 1);
+            if (cons_seen < use + R + 1) gf_ws_wait(cons_own, use + R + 1);
             if (st.sp >= 0 && mm < R) {                                    // ... and of the start partner (its row -1-mm)
                 const int usep = 2 * R - mm < n_last_sp ? 2 * R - mm : n_last_sp;
                 gf_ws_wait(cons_sp, usep + R + 1);
@@ -452,7 +596,7 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
 #pragma unroll
             for (int c = 0; c < K / 2; ++c) rp[c * 32] = make_float4(av[2 * c], bv[2 * c], av[2 * c + 1], bv[2 * c + 1]);
         }
-        gf_ws_row_ready<RING>(prod, bars + k * RING, idx, slot, lane);
+        gf_ws_row_ready<RING>(prod, bars + k * G::NBAR, idx, slot, lane);
         slot = slot + 1 == RING ? 0 : slot + 1;
         // ---- optional A / B planes (hGuidedFilter's d_A, d_B): own territory rows, output columns ----
         if (a.A != nullptr && m >= 0 && m < st.L) {
@@ -472,6 +616,10 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
             }
         }
     }
+#if GF_WS_SYNC == 2
+    __syncwarp();
+    if (ROLE != 2 && lane == 0) gf_ws_bar_arrive(bars + k * G::NBAR + 2 * RING);        // "stream finished": every own row is in the ring
+#endif
 }
 
 // ---- stage 2: consumer warp -------------------------------------------------------------------------
@@ -511,7 +659,7 @@ __device__ __forceinline__ void gf_ws_stage2(const GfWsArgs& a, const GfWsPlan<N
         else if (n >= st.L && st.ep >= 0) { t = st.ep; idx = ep_last - n; }
         base = rings + (t * RING + idx % RING) * G::ROW_F4 + lane;
         prod = ctrl + 2 * t;
-        bar = bars + t * RING;
+        bar = bars + t * G::NBAR;
     };
     auto ld_guide = [&](int i, float (&g)[K]) {
         const int y = st.ys + st.d * i;
@@ -534,7 +682,7 @@ __device__ __forceinline__ void gf_ws_stage2(const GfWsArgs& a, const GfWsPlan<N
     for (int n = -R; n <= n_last; ++n) {
         const float4* nb; const volatile int* np; const unsigned long long* nbar; int ni;
         resolve(n, nb, np, nbar, ni);
-        gf_ws_row_wait<RING>(np, nbar, ni);
+        gf_ws_row_wait<RING>(np, nbar, ni, n >= st.L && st.ep >= 0);
         float4 nw[K / 2];
 #pragma unroll
         for (int c = 0; c < K / 2; ++c) nw[c] = nb[c * 32];
@@ -589,36 +737,62 @@ __device__ __forceinline__ void gf_ws_stage2(const GfWsArgs& a, const GfWsPlan<N
     }
 }
 
-// ---- kernel: one CTA = one (frame, strip, band); warps [0, NS) produce, [NS, 2 NS) consume ------------
-template <int R, int K, int NS, bool TRUNC>
-__global__ void __launch_bounds__(64 * NS, 1) gf_ws_gray_kernel(const GF_GRID_CONSTANT GfWsArgs a)
+// ---- kernel: one CTA = one (frame, strip, band) ---------------------------------------------------------
+// SPLIT = false: warps [0, NS) produce, [NS, 2 NS) consume.  SPLIT = true: [0, NS) sums + solve, [NS, 2 NS) products,
+// [2 NS, 3 NS) consume (warp w, NS + w, 2 NS + w of a 4-stream CTA share a scheduler).
+template <int R, int K, int NS, bool TRUNC, bool SPLIT>
+__global__ void __launch_bounds__((SPLIT ? 96 : 64) * NS, 1) gf_ws_gray_kernel(const GF_GRID_CONSTANT GfWsArgs a)
 {
     using G = GfWsGeom<R, K, NS>;
     GF_DYN_SMEM(float4, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     volatile int* ctrl = reinterpret_cast<volatile int*>(smem + (size_t)NS * G::RING * G::ROW_F4);
     const long item = (long)blockIdx.x;
-    const long per_frame = (long)a.nstrips * a.nbands;
+    // items of a frame: (optionally) the two edge strips first, in their own shorter bands -- their producers run the
+    // mirror code and take longer per row --, then the other strips band by band (strips of one band run side by side:
+    // their halos hit in L2)
+    const bool two = a.nbands_e > 0;
+    const long per_frame = two ? 2L * a.nbands_e + (long)(a.nstrips - 2) * a.nbands : (long)a.nstrips * a.nbands;
     const int64_t f = item / per_frame;
     const int rem = (int)(item % per_frame);
-    const int band = rem / a.nstrips, strip = rem % a.nstrips;       // strips of one band run side by side (halo hits in L2)
-    const int y0 = a.out_y0 + band * a.hb;
-    const int y1 = y0 + a.hb < a.out_y0 + a.out_rows ? y0 + a.hb : a.out_y0 + a.out_rows;
+    int band, strip, hbw;
+    if (two && rem < 2 * a.nbands_e) { band = rem >> 1; strip = (rem & 1) ? a.nstrips - 1 : 0; hbw = a.hb_e; }
+    else if (two) { const int q = rem - 2 * a.nbands_e; band = q / (a.nstrips - 2); strip = 1 + q % (a.nstrips - 2); hbw = a.hb; }
+    else { band = rem / a.nstrips; strip = rem % a.nstrips; hbw = a.hb; }
+    const int y0 = a.out_y0 + band * hbw;
+    const int y1 = y0 + hbw < a.out_y0 + a.out_rows ? y0 + hbw : a.out_y0 + a.out_rows;
     if (threadIdx.x < 2 * NS) ctrl[threadIdx.x] = 0;
-    if (threadIdx.x < NS * G::RING) gf_ws_bar_init(reinterpret_cast<unsigned long long*>(const_cast<int*>(ctrl) + 16) + threadIdx.x);
+    if (threadIdx.x < NS * G::NBAR) gf_ws_bar_init(reinterpret_cast<unsigned long long*>(const_cast<int*>(ctrl) + 16) + threadIdx.x);
     __syncthreads();
     GfWsPlan<NS> pl;
     gf_ws_plan<R, NS>(y0, y1, pl);
-    const int xl = strip * G::WOUT - G::HALO;
+    // strips tile the width in steps of WOUT; the LAST one is pulled back so that its window ends exactly HALO columns
+    // past the image (its mirror is then the compile-time twin of the first strip's) and writes only the columns
+    // the strip before it left over
     const int out_lo = strip * G::WOUT;
     const int out_hi = out_lo + G::WOUT < a.width ? out_lo + G::WOUT : a.width;
-    const int k = warp < NS ? warp : warp - NS;
+    int xl = strip * G::WOUT - G::HALO;
+    if (strip == a.nstrips - 1 && a.nstrips > 1 && a.width + G::HALO - G::WIN >= 0) xl = a.width + G::HALO - G::WIN;
+    const int k = warp % NS, part = warp / NS;
     if (k >= pl.n) return;
-    if (warp < NS) {
-        if (xl >= 0 && xl + G::WIN <= a.width) gf_ws_stage1<R, K, NS, TRUNC, false>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);
-        else gf_ws_stage1<R, K, NS, TRUNC, true>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);
+    const bool in_l = xl >= 0, in_r = xl + G::WIN <= a.width;
+    const int em = (in_l && in_r) ? 0 : ((xl == -G::HALO && in_r) ? 1 : ((in_l && xl + G::WIN == a.width + G::HALO) ? 2 : 3));
+#define GF_WS_S1(ROLE)                                                                                                   \
+    do {                                                                                                                 \
+        if (em == 0) gf_ws_stage1<R, K, NS, TRUNC, 0, ROLE>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);            \
+        else if (em == 1) gf_ws_stage1<R, K, NS, TRUNC, 1, ROLE>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);       \
+        else if (em == 2) gf_ws_stage1<R, K, NS, TRUNC, 2, ROLE>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);       \
+        else gf_ws_stage1<R, K, NS, TRUNC, 3, ROLE>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);                    \
+    } while (0)
+    if (SPLIT) {
+        if (part == 0) GF_WS_S1(1);
+        else if (part == 1) GF_WS_S1(2);
+        else gf_ws_stage2<R, K, NS, TRUNC>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);
+    } else {
+        if (part == 0) GF_WS_S1(0);
+        else gf_ws_stage2<R, K, NS, TRUNC>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);
     }
-    else gf_ws_stage2<R, K, NS, TRUNC>(a, pl, k, lane, f, xl, out_lo, out_hi, smem, ctrl);
+#undef GF_WS_S1
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -628,28 +802,44 @@ __global__ void __launch_bounds__(64 * NS, 1) gf_ws_gray_kernel(const GF_GRID_CO
 #ifndef GF_WS_DEFAULT
 #define GF_WS_DEFAULT 0
 #endif
+// Producer split over two warps (option GF_WS_SPLIT1 overrides)
+#ifndef GF_WS_SPLIT1_DEFAULT
+#define GF_WS_SPLIT1_DEFAULT 0
+#endif
 #ifndef GF_WS_MAX_SUB
 #define GF_WS_MAX_SUB 512
 #endif
 
-// Band height: CTAs run in waves of `sms` (one CTA per SM); a CTA's time ~ its slowest stream:
-//   (hb + 2 x 0.85 R outer rows) / NS  +  2R warm-up rows at ~0.2  +  ~2 rows of start-up.
+// Band heights: CTAs run in waves of `sms` (one CTA per SM); a CTA's time ~ its slowest stream:
+//   (hb + 2 x 0.85 R outer rows) / NS  +  2R warm-up rows at ~0.2  +  ~2 rows of start-up,
+// times `edge_pct` % for the first and the last strip (mirror shuffles in the producer, measured ~1.35x per row:
+// profiles/r2_ws_edge_rows.txt), which therefore get their own, shorter bands.
+struct GfWsBands { int hb, nbands, hb_e, nbands_e; };
 template <int R, int NS>
-static inline int gf_ws_pick_band(int rows, long nstrips_x_count, int sms)
+static inline GfWsBands gf_ws_pick_bands(int rows, int nstrips, long count, int sms, int edge_pct)
 {
     const int hb_min = NS * (R + 1) + 2 * R;
-    int best_hb = rows;
-    double best = 1e300;
+    auto cost = [](int hb) { return (hb + 1.7 * R) / NS + 0.4 * R + 2.0; };
+    GfWsBands best{rows, 1, 0, 0};
+    double best_t = 1e300;
+    const bool edges = nstrips >= 3 && edge_pct > 100;
     for (int nb = 1; nb <= 4096; ++nb) {
-        int hb = (rows + nb - 1) / nb;
+        const int hb = (rows + nb - 1) / nb;
         if (hb < hb_min && nb > 1) break;
         if (hb > NS * GF_WS_MAX_SUB) continue;
-        const long items = nstrips_x_count * ((rows + hb - 1) / hb);
-        const long waves = (items + sms - 1) / sms;
-        const double cost = (double)waves * ((hb + 1.7 * R) / NS + 0.4 * R + 2.0);
-        if (cost < best * 0.999) { best = cost; best_hb = hb; }
+        const int nbr = (rows + hb - 1) / hb;
+        for (int nbe = nbr; nbe <= (edges ? 2 * nbr : nbr); ++nbe) {
+            const int hbe = (rows + nbe - 1) / nbe;
+            if (nbe > nbr && hbe < hb_min) break;
+            const int nber = (rows + hbe - 1) / hbe;
+            const long items = count * (edges ? 2L * nber + (long)(nstrips - 2) * nbr : (long)nstrips * nbr);
+            const long waves = (items + sms - 1) / sms;
+            const double ti = cost(hb), te = edges ? cost(hbe) * edge_pct / 100.0 : 0.0;
+            const double t = (double)waves * (ti > te ? ti : te);
+            if (t < best_t * 0.999) { best_t = t; best = GfWsBands{hb, nbr, edges && nber != nbr ? hbe : 0, edges && nber != nbr ? nber : 0}; }
+        }
     }
-    return best_hb;
+    return best;
 }
 
 template <int R, int K, int NS>
@@ -667,24 +857,26 @@ static const char* gf_ws_launch(const Job& j)
     a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
     a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
     a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
-    int hb = gf_ws_pick_band<R, NS>(j.out_rows, (long)a.nstrips * j.count, sms);
-    hb = GF_KNOB("GF_WS_HB", hb);
-    if (hb > j.out_rows) hb = j.out_rows;
-    if (hb < 1) hb = 1;
-    a.hb = hb;
-    a.nbands = (j.out_rows + hb - 1) / hb;
-    const long items = (long)a.nstrips * a.nbands * j.count;
-    dim3 grid((unsigned)items), block(64 * NS);
-    const char* e;
-    if (j.border == GF_TRUNCATE) {
-        auto kf = gf_ws_gray_kernel<R, K, NS, true>;
-        if ((e = gf_rt_set_smem(kf, G::smem_bytes))) return e;
-        GF_LAUNCH(kf, grid, block, G::smem_bytes, j.stream, a);
-    } else {
-        auto kf = gf_ws_gray_kernel<R, K, NS, false>;
-        if ((e = gf_rt_set_smem(kf, G::smem_bytes))) return e;
-        GF_LAUNCH(kf, grid, block, G::smem_bytes, j.stream, a);
+    GfWsBands bd = gf_ws_pick_bands<R, NS>(j.out_rows, a.nstrips, j.count, sms, GF_KNOB("GF_WS_EDGE_PCT", 135));
+    if (GF_KNOB_SET("GF_WS_HB")) {
+        int hb = GF_KNOB("GF_WS_HB", bd.hb);
+        hb = hb > j.out_rows ? j.out_rows : (hb < 1 ? 1 : hb);
+        bd = GfWsBands{hb, (j.out_rows + hb - 1) / hb, 0, 0};
     }
+    a.hb = bd.hb; a.nbands = bd.nbands; a.hb_e = bd.hb_e; a.nbands_e = bd.nbands_e;
+    const long items = (a.nbands_e > 0 ? 2L * a.nbands_e + (long)(a.nstrips - 2) * a.nbands : (long)a.nstrips * a.nbands) * j.count;
+    const bool split = GF_KNOB("GF_WS_SPLIT1", GF_WS_SPLIT1_DEFAULT) != 0;
+    dim3 grid((unsigned)items), block((split ? 96 : 64) * NS);
+    const char* e;
+#define GF_WS_GO(TR, SP)                                                        \
+    do {                                                                        \
+        auto kf = gf_ws_gray_kernel<R, K, NS, TR, SP>;                          \
+        if ((e = gf_rt_set_smem(kf, G::smem_bytes))) return e;                  \
+        GF_LAUNCH(kf, grid, block, G::smem_bytes, j.stream, a);                 \
+    } while (0)
+    if (j.border == GF_TRUNCATE) { if (split) GF_WS_GO(true, true); else GF_WS_GO(true, false); }
+    else { if (split) GF_WS_GO(false, true); else GF_WS_GO(false, false); }
+#undef GF_WS_GO
     return gf_rt_launch_error();
 }
 
@@ -719,12 +911,8 @@ static const char* gf_ws_try(const Job& j, bool* done, const char** name)
 #else
     GF_WS_CASE(8, 12, 4, "ws_r8_k12")
     GF_WS_CASE(8, 8, 6, "ws_r8_k8")
-    GF_WS_CASE(8, 16, 3, "ws_r8_k16")
     GF_WS_CASE(7, 12, 4, "ws_r7_k12")
-    GF_WS_CASE(7, 8, 6, "ws_r7_k8")
     GF_WS_CASE(4, 8, 6, "ws_r4_k8")
-    GF_WS_CASE(5, 8, 6, "ws_r5_k8")
-    GF_WS_CASE(6, 8, 6, "ws_r6_k8")
     GF_WS_CASE(16, 12, 2, "ws_r16_k12")
     GF_WS_CASE(16, 8, 3, "ws_r16_k8")
 #endif

@@ -142,6 +142,81 @@ def filter_strip_overlapped(api, I_buf: torch.Tensor, p_buf: torch.Tensor, q_out
     run(hi, y1)
 
 
+# ---- row strips with the exchange behind the C ABI (gf_run_strips): peer-mapped strip buffers ----------------
+class DeviceBuffer:
+    """A gf_device_alloc'ed (cudaMalloc) float32 matrix: exportable over CUDA IPC, viewable as a torch tensor."""
+
+    def __init__(self, api, rows: int, cols: int):
+        self.api, self.rows, self.cols = api, rows, cols
+        p = ctypes.c_void_p()
+        api.call("gf_device_alloc", ctypes.addressof(p), rows * cols * 4)
+        self.ptr = p.value
+        self.__cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<f4", "data": (self.ptr, False), "version": 2}
+
+    def tensor(self) -> torch.Tensor:
+        return torch.as_tensor(self, device="cuda")
+
+    def ipc_handle(self) -> bytes:
+        h = ctypes.create_string_buffer(64)
+        self.api.call("gf_ipc_export", ctypes.c_void_p(self.ptr), h)
+        return h.raw
+
+    def free(self):
+        if self.ptr:
+            self.api.call("gf_device_free", ctypes.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+class PeerStrips:
+    """The strip buffers of one rank (guide + src, with room for the 2r halos) and the neighbours' buffers mapped
+    into this process over CUDA IPC.  `run` is ONE C call per image: gf_run_strips pulls the halo rows from the
+    neighbours with peer copies and launches the strip kernel (include/gf_b200.h)."""
+
+    def __init__(self, api, height: int, width: int, rank: int, world: int, r: int, group=None):
+        from ._capi import StripPeer
+        self.api, self.height, self.width, self.rank, self.world, self.r = api, height, width, rank, world, r
+        self.y0, self.y1 = strip_rows(height, rank, world)
+        top, bot = ctypes.c_int(), ctypes.c_int()
+        api.call("gf_strip_layout", height, self.y0, self.y1 - self.y0, r, ctypes.addressof(top), ctypes.addressof(bot))
+        self.top, self.bot = top.value, bot.value
+        rows = self.top + (self.y1 - self.y0) + self.bot
+        self.guide, self.src = DeviceBuffer(api, rows, width), DeviceBuffer(api, rows, width)
+        self.own_guide = self.guide.tensor()[self.top:self.top + (self.y1 - self.y0)]
+        self.own_src = self.src.tensor()[self.top:self.top + (self.y1 - self.y0)]
+        self._opened = []
+        self.up = self.down = None
+        if world > 1:
+            mine = (self.guide.ipc_handle(), self.src.ipc_handle(), self.top, self.y1 - self.y0)
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine, group=group)
+
+            def peer(k):
+                hg, hs, ptop, prows = everyone[k]
+                pg, ps = ctypes.c_void_p(), ctypes.c_void_p()
+                api.call("gf_ipc_open", hg, ctypes.addressof(pg))
+                api.call("gf_ipc_open", hs, ctypes.addressof(ps))
+                self._opened += [pg.value, ps.value]
+                return StripPeer(pg.value, ps.value, width, width, ptop, prows)
+            if rank > 0:
+                self.up = peer(rank - 1)
+            if rank < world - 1:
+                self.down = peer(rank + 1)
+
+    def run(self, q_out: torch.Tensor, eps: float, border: int, stream: Optional[int] = None) -> None:
+        self.api.call("gf_run_strips", ctypes.c_void_p(self.guide.ptr), ctypes.c_void_p(self.src.ptr), q_out.data_ptr(), self.width,
+                      self.height, self.y0, self.y1 - self.y0, self.width, self.width, q_out.stride(0), self.r, eps, border,
+                      ctypes.byref(self.up) if self.up is not None else None,
+                      ctypes.byref(self.down) if self.down is not None else None,
+                      ctypes.c_void_p(stream) if stream else None)
+
+    def close(self):
+        for p in self._opened:
+            self.api.call("gf_ipc_close", ctypes.c_void_p(p))
+        self._opened = []
+        self.guide.free()
+        self.src.free()
+
+
 def filter_frames(api, I: torch.Tensor, p: torch.Tensor, q: torch.Tensor, r: int, eps: float, border: int,
                   stream: Optional[int] = None) -> None:
     """Filters this rank's block of frames with ONE launch.  I: [n,h,w] (gray) or [n,h,w,3]

@@ -110,6 +110,42 @@ int gf_guided_gray_strip(const float* guide, const float* src, float* dst, int w
 
 /* ---- the five path-A launchers (GuidedFilter/guided_filter_d.h:6-18) ----------------------- */
 
+/* ---- row strips of ONE huge image over the GPUs of a node, halo exchange inside the call -----------------
+   (BASELINE configs[4]; SURVEY 8(b) "gf_run_strips"; the reference is single-GPU, main.cpp:17, so there is no
+   reference interface to cite -- this is the C-host form of what cudaimageprocessing_b200/dist.py does in Python.)
+
+   Rank g owns image rows [y0, y0 + rows).  Its strip buffers (guide_buf, src_buf) hold
+       `top` halo rows | the `rows` own rows | `bot` halo rows          (gf_strip_layout: top/bot = 2r, clipped
+   at the image's real top and bottom, where the border rule applies instead), so buffer row 0 is image row y0 - top.
+   `up` / `down` describe the strip buffers of the rank above / below AS SEEN FROM THIS DEVICE: device pointers to THEIR
+   buffer row 0 (the same process with peer access enabled, or another process's gf_device_alloc'ed buffer opened with
+   gf_ipc_open), their strides, their own `top` and `rows`.  The call PULLS the halo rows it needs straight out of the
+   neighbours' own rows -- four strided peer copies on `stream` (copy engines over NVLink: no SM time, no NCCL,
+   no staging) -- and launches the strip kernel behind them on the same stream.
+   up == NULL / down == NULL: that halo (if the layout has one) is already in the buffer, e.g. after an
+   ncclSend/ncclRecv exchange done by the caller (dist.exchange_halos_inplace).
+   Ordering across ranks is the caller's: the neighbours' own rows must be complete before the call and unchanged
+   until `stream` has passed it (one barrier / IPC event on either side; bench.py).  GF_ERR_INVALID if a neighbour
+   strip is shorter than the halo it must supply. */
+typedef struct gf_strip_peer {
+    const float* guide;
+    const float* src;
+    int64_t guide_stride, src_stride;      /* floats; 0 = width */
+    int top;                               /* halo rows above the neighbour's own rows in ITS buffers */
+    int rows;                              /* the neighbour's own rows */
+} gf_strip_peer;
+int gf_strip_layout(int global_height, int y0, int rows, int r, int* top, int* bot);
+int gf_run_strips(float* guide_buf, float* src_buf, float* dst, int width, int global_height, int y0, int rows,
+                  int64_t guide_stride, int64_t src_stride, int64_t dst_stride, int r, float eps, int border,
+                  const gf_strip_peer* up, const gf_strip_peer* down, void* stream);
+/* Device buffers that other ranks of the node can map: cudaMalloc'ed (IPC exports allocation bases only), the
+   64-byte cudaIpcMemHandle_t of one, and mapping / unmapping a neighbour's. */
+int gf_device_alloc(void** ptr, size_t bytes);
+int gf_device_free(void* ptr);
+int gf_ipc_export(const void* ptr, void* handle64);
+int gf_ipc_open(const void* handle64, void** ptr);
+int gf_ipc_close(void* ptr);
+
 /* hBoxFilter (guided_filter_d.cu:868-924): box mean of a `channels`-interleaved image.  One
    streaming kernel with exact window sums; no integral image, so no `integral` scratch.
    In-place (src == dst) is allowed, as in the reference (guided_filter.cpp:59-60). */

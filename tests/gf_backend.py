@@ -98,6 +98,36 @@ class _Base:
         self.sync()
         return self.down(dq)
 
+    def run_strips(self, I, p, world, r, eps, border):
+        """gf_run_strips with `world` ranks emulated in ONE process: every rank's strip buffers hold only its own
+        rows (halo rows poisoned), the call pulls the halos out of the neighbours' buffers."""
+        from cudaimageprocessing_b200._capi import StripPeer
+        H, w = I.shape
+        ranks = []
+        for g in range(world):
+            y0, y1 = H * g // world, H * (g + 1) // world
+            top, bot = ctypes.c_int(), ctypes.c_int()
+            self.api.call("gf_strip_layout", H, y0, y1 - y0, r, ctypes.addressof(top), ctypes.addressof(bot))
+            bufs = []
+            for a in (I, p):
+                b = np.full((top.value + y1 - y0 + bot.value, w), np.nan, np.float32)
+                b[top.value:top.value + y1 - y0] = a[y0:y1]
+                bufs.append(self.up(b))
+            ranks.append((y0, y1, top.value, bufs))
+        out = np.empty_like(I)
+        for g, (y0, y1, top, bufs) in enumerate(ranks):
+            def peer(k):
+                py0, py1, ptop, pb = ranks[k]
+                return StripPeer(self.ptr(pb[0]), self.ptr(pb[1]), w, w, ptop, py1 - py0)
+            up = peer(g - 1) if g > 0 else None
+            dn = peer(g + 1) if g < world - 1 else None
+            dq = self.empty((y1 - y0, w))
+            self.api.call("gf_run_strips", self.ptr(bufs[0]), self.ptr(bufs[1]), self.ptr(dq), w, H, y0, y1 - y0, w, w, w, r, eps, border,
+                          ctypes.byref(up) if up is not None else None, ctypes.byref(dn) if dn is not None else None, None)
+            self.sync()
+            out[y0:y1] = self.down(dq)
+        return out
+
     def box(self, a, r, border, inplace=False):
         h, w = a.shape[:2]
         c = 1 if a.ndim == 2 else a.shape[2]

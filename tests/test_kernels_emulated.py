@@ -314,3 +314,81 @@ def test_class_run_planar_path(be):
         q = be.class_run(I, s3, 4, 0.05)
         assert be.api.last_kernel() == "s8_r4"
         assert np.abs(q - O.guided_filter_class_run(I, s3, 4, 0.05)).max() <= TOL
+
+
+# ---- the warp-specialised kernel (gf_ws.cuh: K columns per lane, producer / consumer warps) under the emulator ----
+@pytest.mark.parametrize("shape,r,border,k", [
+    ((90, 704), 8, 0, 12),      # two strips (first + pulled-back last), one band, four streams sharing boundary rows
+    ((300, 1100), 8, 2, 12),    # REFLECT mirror constants, several bands (the emulated device has 4 SMs)
+    ((60, 1100), 8, 1, 12),     # TRUNCATE: zeroed outside columns, per-pixel counts
+    ((60, 1060), 8, 0, 12),     # last strip overlaps its neighbour by more than a lane
+    ((37, 356), 8, 0, 12),      # one strip that overhangs both edges (gathered loads), too few rows for 4 streams
+    ((53, 1060), 8, 1, 12),     # TRUNCATE with short bands: streams at the image top and bottom
+    ((130, 704), 8, 0, 8),      # K = 8 (32-byte loads), six streams
+    ((95, 704), 8, 1, 8),
+    ((200, 704), 4, 0, 8),      # r = 4: window narrower than two lanes
+    ((210, 400), 16, 0, 12),    # r = 16: windows reach two lanes to either side, two streams
+    ((100, 800), 16, 2, 12),
+])
+@pytest.mark.parametrize("split", [0, 1])
+def test_gray_ws(be, shape, r, border, k, split, knob):
+    """split = 1: the producer of every stream is two warps (sums + solve / products) that meet in the ring slot."""
+    knob(be, "GF_WS", 1)
+    knob(be, "GF_WS_K", k)
+    knob(be, "GF_WS_SPLIT1", split)
+    I, p = synth_pair(*shape, seed=81, kind="structured")
+    q, A, B = be.guided_gray(I, p, r, 1e-2, border, want_ab=True)
+    assert be.api.last_kernel() == f"ws_r{r}_k{k}"
+    rq, ra, rb = O.guided_filter_gray(I, p, r, 1e-2, border, np.float64, return_ab=True)
+    assert np.abs(q - rq).max() <= TOL
+    assert np.abs(A - ra).max() <= TOL and np.abs(B - rb).max() <= TOL
+    q2 = be.guided_gray(I, p, r, 1e-2, border)              # without the A / B planes: the same q
+    assert np.array_equal(q, q2)
+
+
+@pytest.mark.parametrize("hb", [41, 64, 150])
+def test_gray_ws_band_heights(be, hb, knob):
+    """forced band heights: 4, 3, 2 and 1 streams per CTA, last band shorter than the others"""
+    knob(be, "GF_WS", 1)
+    knob(be, "GF_WS_HB", hb)
+    I, p = synth_pair(170, 720, seed=83)
+    q = be.guided_gray(I, p, 8, 1e-2, 0)
+    assert be.api.last_kernel() == "ws_r8_k12"
+    assert np.abs(q - O.guided_filter_gray(I, p, 8, 1e-2, 0, np.float64)).max() <= TOL
+
+
+def test_gray_ws_strip_and_batch(be, knob):
+    """the strip entry (buffer = rows + 2r halos of a taller image) and a batch of frames through the ws kernel"""
+    knob(be, "GF_WS", 1)
+    rng = np.random.default_rng(85)
+    Hh, w, r = 260, 704, 8
+    I = rng.random((Hh, w), dtype=np.float32)
+    p = rng.random((Hh, w), dtype=np.float32)
+    ref = O.guided_filter_gray(I, p, r, 1e-2, 0, np.float64)
+    y0, y1 = 90, 180
+    lo, hi = y0 - 2 * r, y1 + 2 * r
+    q = be.strip(I[lo:hi], p[lo:hi], w, Hh, lo, y0, y1 - y0, r, 1e-2, 0)
+    assert be.api.last_kernel() == "ws_r8_k12"
+    assert np.abs(q - ref[y0:y1]).max() <= TOL
+    q = be.strip(I[:y1 + 2 * r], p[:y1 + 2 * r], w, Hh, 0, 0, y1, r, 1e-2, 0)       # strip at the image top: border rule above
+    assert np.abs(q - ref[:y1]).max() <= TOL
+    Ib = rng.random((3, 70, 704), dtype=np.float32)
+    pb = rng.random((3, 70, 704), dtype=np.float32)
+    qb = be.batch(Ib, pb, r, 1e-2, 0)
+    for i in range(3):
+        assert np.abs(qb[i] - O.guided_filter_gray(Ib[i], pb[i], r, 1e-2, 0, np.float64)).max() <= TOL
+
+
+@pytest.mark.parametrize("world,border", [(2, 0), (3, 1), (4, 2)])
+def test_run_strips_pulls_halos(be, world, border):
+    """gf_run_strips: every rank's buffers hold its own rows only; the call pulls the 2r halo rows out of
+    the neighbours' buffers and filters the strip -- the stitched result equals the single-image result."""
+    I, p = synth_pair(97, 130, seed=91, kind="structured")
+    q = be.run_strips(I, p, world, 3, 1e-2, border)
+    assert np.abs(q - O.guided_filter_gray(I, p, 3, 1e-2, border, np.float64)).max() <= TOL
+
+
+def test_run_strips_rejects_short_neighbours(be):
+    I, p = synth_pair(40, 64, seed=92)
+    with pytest.raises(Exception, match="shorter than"):
+        be.run_strips(I, p, 8, 4, 1e-2, 0)          # 5-row strips cannot supply 8 halo rows
