@@ -209,6 +209,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-scaling", action="store_true", help="skip the config-3 / config-5 legs (scaling_configs)")
+    ap.add_argument("--frames", type=int, default=256, help="config 3: frames in the batch (sharded over the ranks)")
+    ap.add_argument("--giga", type=int, default=32768, help="config 5: side of the square image (sharded by row strips)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -335,6 +338,21 @@ def main():
     torch.cuda.synchronize()
     e2e_ok = bool(np.abs(hq - frames[0][2].cpu().numpy()).max() <= 1e-6)
 
+    ref_gpu = reference_gpu_numbers(torch, frames) if (world == 1 and rank == 0) else None
+
+    # ---- the north_star's two multi-GPU splits (BASELINE configs[2], configs[4]); every rank takes part
+    scaling_configs = None
+    if not args.no_scaling:
+        from bench_tools import legs
+        del frames
+        torch.cuda.empty_cache()
+        scaling_configs = {}
+        try:
+            scaling_configs["config3_batch_1080p_colour_r16"] = legs.config3(torch, dist, api, pkg, rank, world, barrier, frames=args.frames)
+            scaling_configs["config5_giga_strips_r16"] = legs.config5(torch, dist, api, pkg, rank, world, barrier, size=args.giga)
+        except Exception as e:      # never lose the headline line over a leg
+            scaling_configs["error"] = f"{type(e).__name__}: {e}"
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,6 +376,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if scaling_configs is not None:
+        line["scaling_configs"] = scaling_configs
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -368,9 +388,8 @@ def main():
         if not args.no_cpu:
             res = cpu_port_bench(steps=30, warmup=2, budget_s=12.0, frames=host[0])
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        rg = reference_gpu_numbers(torch, frames)
-        if rg:
-            line["reference_gpu"] = rg
+        if ref_gpu:
+            line["reference_gpu"] = ref_gpu
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

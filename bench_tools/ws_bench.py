@@ -101,6 +101,12 @@ def main():
             jobs.append(({"GF_WS": "1", "GF_WS_K": "12", "GF_WS_SPLIT1": "1", "GF_WS_EDGE_PCT": str(pct)}, (3840, 2160, 8)))
         jobs += [({"GF_WS": "1", "GF_WS_SPLIT1": "1"}, (3840, 2160, 16)), ({"GF_WS": "1", "GF_WS_SPLIT1": "1", "GF_WS_K": "8"}, (3840, 2160, 16)),
                  ({"GF_WS": "1", "GF_WS_SPLIT1": "1"}, (3840, 2160, 4)), ({"GF_WS": "1", "GF_WS_SPLIT1": "1"}, (3840, 2160, 8, 1))]
+    if len(sys.argv) > 1 and sys.argv[1] == "--edge":          # weight of the edge strips in the band chooser
+        jobs = []
+        for k in (12, 8):
+            for pct in (135, 160, 185, 210, 240):
+                for c in ((3840, 2160, 8), (7680, 4320, 8)):
+                    jobs.append(({"GF_WS": "1", "GF_WS_K": str(k), "GF_WS_EDGE_PCT": str(pct)}, c))
     if len(sys.argv) > 1 and sys.argv[1] == "--variants":      # differently compiled builds: ws_bench.py --variants libA.so libB.so ...
         libs = sys.argv[2:]
         jobs = []

@@ -16,6 +16,7 @@
 #include "gf_pointwise.cuh"
 #include "gf_integral.cuh"
 #include "gf_gauss.cuh"
+#include "gf_scan.cuh"
 #include "gf_rt.h"
 #ifdef GF_HAVE_FAST
 #include "gf_fast.cuh"
@@ -171,10 +172,106 @@ bool overlaps(const Plane& a, const Plane& b, int rows, int count)
     return a.ptr < b1 && b.ptr < a1;
 }
 
+// ---- scan path (gf_scan.cuh): any radius, full frames, gray ------------------------------------------------
+static bool scan_ok(const Job& j)
+{
+    if (j.color || j.guide.channels != 1 || j.src.channels != 1 || j.dst.channels != 1 || j.guide.coff || j.src.coff || j.dst.coff) return false;
+    if (j.buf_y0 != 0 || j.out_y0 != 0 || j.buf_rows != j.height || j.out_rows != j.height) return false;     // full frames only
+    return j.r >= 1 && (j.border == GF_TRUNCATE || (j.r < j.width && j.r < j.height));                       // single reflections (TRUNCATE: any radius)
+}
+
+// box mean of plane `a` (or of a*b) into `out`, through the row-prefix scratch P
+static const char* scan_box(const float* a, int64_t sa, const float* b, int64_t sb, float* out, int64_t so, double* P, int w, int h, int r,
+                            int border, void* stream)
+{
+    GfScanPrefixArgs pa;
+    pa.a = a; pa.b = b; pa.P = P; pa.width = w; pa.height = h; pa.sa = sa; pa.sb = sb; pa.sp = w;
+    dim3 g1(h < 8192 ? h : 8192), b1(256);
+    if (b) { auto k = gf_rowprefix_kernel<1>; GF_LAUNCH(k, g1, b1, 0, stream, pa); }
+    else { auto k = gf_rowprefix_kernel<0>; GF_LAUNCH(k, g1, b1, 0, stream, pa); }
+    GfScanBoxArgs ba;
+    ba.P = P; ba.out = out; ba.width = w; ba.height = h; ba.r = r; ba.border = border; ba.sp = w; ba.so = so;
+    // bands: enough CTAs to fill the GPU, but tall enough that the 2r-row warm-up of a band stays below half its rows
+    int sms = 148, mj = 0, mn = 0;
+    gf_rt_device_info(&sms, &mj, &mn);
+    const int cols = div_up(w, 128);
+    int nb = div_up(8 * sms, cols);
+    int hb = div_up(h, nb < 1 ? 1 : nb);
+    if (hb < 2 * r) hb = 2 * r;
+    if (hb > h) hb = h;
+    ba.hb = hb;
+    dim3 g2(cols, div_up(h, hb)), b2(128);
+    auto k2 = gf_boxcols_kernel;
+    GF_LAUNCH(k2, g2, b2, 0, stream, ba);
+    return gf_rt_launch_error();
+}
+
+static int run_scan_gray(const Job& j)
+{
+    const int w = j.width, h = j.height;
+    const size_t n = (size_t)w * h;
+    void* scratch = nullptr;
+    if (const char* e = gf_rt_alloc_async(&scratch, n * (8 + 4 * 4), j.stream)) return fail(GF_ERR_NOMEM, "scan-path scratch (%zu bytes): %s", n * 24, e);
+    double* P = (double*)scratch;
+    float* im = (float*)(P + n), *pm = im + n, *ipm = pm + n, *iim = ipm + n;
+    const char* e = nullptr;
+    for (int f = 0; f < j.count && !e; ++f) {
+        const float* I = j.guide.ptr + f * j.guide.frame_stride;
+        const float* p = j.src.ptr + f * j.src.frame_stride;
+        float* q = const_cast<float*>(j.dst.ptr) + f * j.dst.frame_stride;
+        if (!e) e = scan_box(I, j.guide.stride, nullptr, 0, im, w, P, w, h, j.r, j.border, j.stream);
+        if (!e) e = scan_box(p, j.src.stride, nullptr, 0, pm, w, P, w, h, j.r, j.border, j.stream);
+        if (!e) e = scan_box(I, j.guide.stride, p, j.src.stride, ipm, w, P, w, h, j.r, j.border, j.stream);
+        if (!e) e = scan_box(I, j.guide.stride, I, j.guide.stride, iim, w, P, w, h, j.r, j.border, j.stream);
+        if (!e) {
+            GfScanAbArgs ab;
+            ab.im = im; ab.pm = pm; ab.ipm_a = ipm; ab.iim_b = iim; ab.width = w; ab.height = h; ab.s = w; ab.eps = j.eps;
+            dim3 g(div_up(w, 256), h < 1024 ? h : 1024), b(256);
+            auto k = gf_scan_ab_kernel;
+            GF_LAUNCH(k, g, b, 0, j.stream, ab);
+            e = gf_rt_launch_error();
+        }
+        if (!e && j.A.ptr) {
+            float* A = const_cast<float*>(j.A.ptr) + f * j.A.frame_stride;
+            float* B = const_cast<float*>(j.B.ptr) + f * j.B.frame_stride;
+            e = gf_rt_copy2d_async(A, j.A.stride * 4, ipm, (size_t)w * 4, (size_t)w * 4, h, j.stream);
+            if (!e) e = gf_rt_copy2d_async(B, j.B.stride * 4, iim, (size_t)w * 4, (size_t)w * 4, h, j.stream);
+        }
+        if (!e) e = scan_box(ipm, w, nullptr, 0, im, w, P, w, h, j.r, j.border, j.stream);       // mean_a -> im
+        if (!e) e = scan_box(iim, w, nullptr, 0, pm, w, P, w, h, j.r, j.border, j.stream);       // mean_b -> pm
+        if (!e) {
+            GfPwArgs a;
+            a.in0 = I; a.in1 = im; a.in2 = pm; a.in3 = nullptr; a.out = q;
+            a.width = w; a.height = h; a.cs = 1; a.cg = 1; a.ss = w; a.sg = j.guide.stride; a.eps = 0.f;
+            // q = I * mean_a + mean_b: the source-shaped operands (mean_a, mean_b, q) share ONE stride in the kernel, so a
+            // pitched destination goes through a packed temporary row layout only when it has to
+            if (j.dst.stride == w) {
+                dim3 g(div_up(w, 256), h < 1024 ? h : 1024), b(256);
+                auto k = gf_pointwise_kernel<GF_PW_LINEAR>;
+                GF_LAUNCH(k, g, b, 0, j.stream, a);
+                e = gf_rt_launch_error();
+            } else {
+                a.out = ipm;
+                dim3 g(div_up(w, 256), h < 1024 ? h : 1024), b(256);
+                auto k = gf_pointwise_kernel<GF_PW_LINEAR>;
+                GF_LAUNCH(k, g, b, 0, j.stream, a);
+                e = gf_rt_launch_error();
+                if (!e) e = gf_rt_copy2d_async(q, j.dst.stride * 4, ipm, (size_t)w * 4, (size_t)w * 4, h, j.stream);
+            }
+        }
+    }
+    gf_rt_free_async(scratch, j.stream);
+    if (e) return fail(GF_ERR_CUDA, "scan path: %s", e);
+    g_launches += 15L * j.count;
+    g_kernel = "scan_gray";
+    return GF_OK;
+}
+
 int run_job(const Job& j)
 {
     int rc = GF_OK;
     bool done = false;
+    if (GF_KNOB("GF_SCAN", 0) && scan_ok(j)) return run_scan_gray(j);      // measurement / tests: force the scan path
 #ifdef GF_HAVE_FAST
     {
         const char* name = nullptr;
@@ -190,6 +287,8 @@ int run_job(const Job& j)
     }
 #endif
     if (!done) rc = j.color ? launch_generic<GfColorModel>(j) : launch_generic<GfGrayModel>(j);
+    // radii the streaming kernels cannot hold (4r halo columns of at most 1024 threads): the scan path takes any radius
+    if (!done && rc == GF_ERR_UNSUPPORTED && scan_ok(j)) rc = run_scan_gray(j);
     return rc;
 }
 
@@ -674,6 +773,18 @@ int gf_box_filter(const float* src, float* dst, int width, int height, int chann
     }
     GenericCfg c;
     rc = plan_generic(jj, 2 * r, 2 * r, channels, 0, &c);
+    if ((rc == GF_ERR_UNSUPPORTED || GF_KNOB("GF_SCAN", 0)) && channels == 1 && r >= 1 && (border == GF_TRUNCATE || (r < width && r < height))) {
+        // any radius: row prefixes + column pass (gf_scan.cuh); the prefix scratch doubles as the in-place temporary
+        void* P = nullptr;
+        if (const char* e = gf_rt_alloc_async(&P, (size_t)width * height * 8, stream)) { if (tmp) gf_rt_free_async(tmp, stream); return fail(GF_ERR_NOMEM, "scan-path scratch: %s", e); }
+        const char* e = scan_box(src, jj.src.stride, nullptr, 0, dst, or_packed(dst_stride, width, 1), (double*)P, width, height, r, border, stream);
+        gf_rt_free_async(P, stream);
+        if (tmp) gf_rt_free_async(tmp, stream);
+        if (e) return fail(GF_ERR_CUDA, "scan box: %s", e);
+        g_launches += 2;
+        g_kernel = "scan_box";
+        return GF_OK;
+    }
     if (rc) { if (tmp) gf_rt_free_async(tmp, stream); return rc; }
     GfArgs a = mk_args(jj);
     a.wc = c.wc; a.hb = c.hb;

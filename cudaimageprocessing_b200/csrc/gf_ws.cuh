@@ -38,7 +38,8 @@
 #define GF_WS_SPLIT 1        // prefix / suffix chains of the window sums in two halves
 #endif
 #ifndef GF_WS_PF
-#define GF_WS_PF 6           // rows ahead for the L2 prefetch hint of the entering row (0 = off)
+#define GF_WS_PF 0           // rows ahead for an L2 prefetch hint of the entering row; measured 4-6 % SLOWER at 4K/8K
+                             // (profiles/r2_ws_variants.jsonl), so off
 #endif
 #ifndef GF_WS_NORM2
 #define GF_WS_NORM2 1        // two-term reciprocal of the pixel count (see GfNorm)

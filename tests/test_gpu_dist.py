@@ -42,6 +42,18 @@ def _worker(rank, world, port, H, W, r, out_dir):
         D.filter_strip(api, bufI, bufP, q, H, rank, world, r, 1e-2, 0)
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, f"q_{rank}.npy"), q.cpu().numpy())
+        # the same strips through the C ABI's own exchange: gf_run_strips pulls the halos out of the neighbours'
+        # IPC-mapped buffers (no NCCL on the data path)
+        ps = D.PeerStrips(api, H, W, rank, world, r)
+        ps.own_guide.copy_(torch.from_numpy(I[y0:y1])); ps.own_src.copy_(torch.from_numpy(p[y0:y1]))
+        torch.cuda.synchronize()
+        dist.barrier()
+        q2 = torch.empty((y1 - y0, W), device="cuda")
+        ps.run(q2, 1e-2, 0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        np.save(os.path.join(out_dir, f"q2_{rank}.npy"), q2.cpu().numpy())
+        ps.close()
         # batch sharding: 6 frames over the ranks, one launch per rank
         n = 6
         f0, f1 = D.shard_frames(n, rank, world)
@@ -70,7 +82,10 @@ def test_strips_and_batches_over_nccl(tmp_path):
     I = rng.random((H, W), dtype=np.float32)
     p = rng.random((H, W), dtype=np.float32)
     q = np.concatenate([np.load(tmp_path / f"q_{k}.npy") for k in range(world)], axis=0)
-    assert np.abs(q - C.guided_gray_f64(I, p, r, 1e-2, 0, 8)).max() <= 1e-4
+    ref = C.guided_gray_f64(I, p, r, 1e-2, 0, 8)
+    assert np.abs(q - ref).max() <= 1e-4
+    q2 = np.concatenate([np.load(tmp_path / f"q2_{k}.npy") for k in range(world)], axis=0)
+    assert np.abs(q2 - ref).max() <= 1e-4          # gf_run_strips (peer-copy exchange inside the C call)
     frames = np.random.default_rng(9).random((6, 96, 160), dtype=np.float32)
     qb = np.concatenate([np.load(tmp_path / f"b_{k}.npy") for k in range(world)], axis=0)
     for k in range(6):

@@ -404,6 +404,34 @@ def test_host_entry_and_dropin_program(be, tmp_path):
             assert np.abs(A - ra).max() <= TOL and np.abs(B - rb).max() <= TOL
 
 
+@pytest.mark.parametrize("world,r", [(2, 8), (3, 16), (5, 4)])
+def test_run_strips_one_gpu(be, world, r):
+    """gf_run_strips with every "rank" on this one GPU (peer pointers = plain device pointers): the halo pull, the
+    strip geometry and the stitched result -- the multi-GPU form of the same call runs in tests/test_gpu_dist.py."""
+    I, p = synth_pair(1500, 1408, seed=23)
+    q = be.run_strips(I, p, world, r, 1e-2, 0)
+    assert np.abs(q - C.guided_gray_f64(I, p, r, 1e-2, 0, NT)).max() <= TOL
+
+
+def test_large_radius_4k_scan_path(be, knob):
+    """r = 256 on a 4K frame through the class API (TRUNCATE) and hGuidedFilter's border (REFLECT101); both take
+    the scan path (row prefixes in float64 + column pass) because no streaming kernel holds a 1024-column halo.
+    Also the scan path forced at r = 8 against the fused kernel."""
+    I, p = synth_pair(2160, 3840, seed=31)
+    for border in (1, 0):
+        q = be.guided_gray(I, p, 256, 1e-2, border)
+        assert be.api.last_kernel() == "scan_gray"
+        assert np.abs(q - C.guided_gray_f64(I, p, 256, 1e-2, border, NT)).max() <= TOL
+    q_fused = be.guided_gray(I, p, 8, 1e-2, 0)
+    knob(be, "GF_SCAN", 1)
+    q_scan = be.guided_gray(I, p, 8, 1e-2, 0)
+    assert be.api.last_kernel() == "scan_gray"
+    assert np.abs(q_scan - q_fused).max() <= 2e-6
+    m = be.box(I, 600, 1)
+    assert be.api.last_kernel() == "scan_box"
+    assert np.abs(m - C.box_mean_f32(I, 600, 1, NT)).max() <= 1e-5
+
+
 def test_against_reference_gpu_code(be):
     """The reference's own GPU sources, compiled unmodified for sm_100a (oracle/_ref): path B
     (hGuidedFilter, r=7) agrees with us to float rounding; path A's float32 integral image is

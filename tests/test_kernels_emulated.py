@@ -392,3 +392,32 @@ def test_run_strips_rejects_short_neighbours(be):
     I, p = synth_pair(40, 64, seed=92)
     with pytest.raises(Exception, match="shorter than"):
         be.run_strips(I, p, 8, 4, 1e-2, 0)          # 5-row strips cannot supply 8 halo rows
+
+
+# ---- the scan path (gf_scan.cuh): float64 row prefixes + column pass, any radius ------------------------------------
+@pytest.mark.parametrize("shape,r,border", [((40, 70), 8, 0), ((40, 70), 8, 1), ((40, 70), 8, 2), ((33, 50), 30, 0), ((33, 50), 32, 1),
+                                            ((64, 2100), 20, 2), ((300, 40), 39, 0)])
+def test_gray_scan_path(be, shape, r, border, knob):
+    """forced through the scan path (GF_SCAN): windows that overhang one or both edges, rows wider than one 2048-column
+    scan chunk, radii close to the image size"""
+    knob(be, "GF_SCAN", 1)
+    I, p = synth_pair(*shape, seed=95, kind="structured")
+    q, A, B = be.guided_gray(I, p, r, 1e-2, border, want_ab=True, pad=3)
+    assert be.api.last_kernel() == "scan_gray"
+    rq, ra, rb = O.guided_filter_gray(I, p, r, 1e-2, border, np.float64, return_ab=True)
+    assert np.abs(q - rq).max() <= TOL and np.abs(A - ra).max() <= TOL and np.abs(B - rb).max() <= TOL
+
+
+def test_large_radius_falls_to_scan_path(be):
+    """r >= 249 used to return GF_ERR_UNSUPPORTED (4r halo columns of at most 1024 threads); the class API
+    (TRUNCATE) and hBoxFilter take any radius in the reference."""
+    I, p = synth_pair(300, 1200, seed=96)
+    q = be.guided_gray(I, p, 256, 1e-2, 1)
+    assert be.api.last_kernel() == "scan_gray"
+    assert np.abs(q - O.guided_filter_gray(I, p, 256, 1e-2, 1, np.float64)).max() <= TOL
+    a = I[:, :1100]
+    m = be.box(np.ascontiguousarray(a), 520, 1)
+    assert be.api.last_kernel() == "scan_box"
+    assert np.abs(m - O.box_mean(a, 520, 1)).max() <= 2e-6
+    m = be.box(np.ascontiguousarray(a), 520, 1, inplace=True)
+    assert np.abs(m - O.box_mean(a, 520, 1)).max() <= 2e-6
