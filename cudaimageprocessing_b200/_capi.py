@@ -30,6 +30,7 @@ SIGNATURES = {
     "gf_ipc_export": (c_int, [P, P]),
     "gf_ipc_open": (c_int, [P, P]),
     "gf_ipc_close": (c_int, [P]),
+    "gf_window_sums_u8": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int64, c_int64, c_int, c_int, P]),
     "gf_box_filter": (c_int, [P, P, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int, P]),
     "gf_multiply": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, P]),
     "gf_calc_a": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_float, P]),

@@ -808,7 +808,11 @@ static const char* gf_s8_try(const Job& j, bool* done, const char** name, bool u
     if (u8) {
         switch (j.r) {
 #define GF_S8_CASE(RR) case RR: *done = true; *name = "s8u8_r" #RR; return gf_s8_launch<RR, unsigned char>(j);
+#ifdef GF_CPU_EMU
         GF_S8_CASE(4) GF_S8_CASE(7) GF_S8_CASE(8) GF_S8_CASE(16)
+#else      // every radius of the reference's sweep (run.py:4-6: r = 1..7) plus the BASELINE radii
+        GF_S8_CASE(1) GF_S8_CASE(2) GF_S8_CASE(3) GF_S8_CASE(4) GF_S8_CASE(5) GF_S8_CASE(6) GF_S8_CASE(7) GF_S8_CASE(8) GF_S8_CASE(16)
+#endif
 #undef GF_S8_CASE
         default: return nullptr;
         }

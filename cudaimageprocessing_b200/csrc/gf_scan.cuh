@@ -15,33 +15,40 @@
 #pragma once
 #include "gf_common.cuh"
 
-struct GfScanPrefixArgs {
-    const float* a; const float* b;     // MODE 1: v = a * b
-    double* P;
+template <class TIn, class TAcc>
+struct GfScanPrefixArgsT {
+    const TIn* a; const TIn* b;         // MODE 1: v = a * b
+    TAcc* P;
     int width, height;
     int64_t sa, sb, sp;                 // row strides (elements)
 };
+typedef GfScanPrefixArgsT<float, double> GfScanPrefixArgs;
+// uint8 planes: exact integer prefixes (north_star: "bit-exact integral sums for uint8 input"); 64-bit accumulators
+// never overflow (255^2 x 2^31 columns < 2^63)
+typedef GfScanPrefixArgsT<unsigned char, long long> GfScanPrefixArgsU8;
 
 // One CTA scans one row at a time (grid-stride over rows): 256 threads x 8 columns per chunk, thread totals scanned
 // through shared memory (Hillis-Steele, float64), carry from chunk to chunk.
-template <int MODE>
-__global__ void __launch_bounds__(256) gf_rowprefix_kernel(const GfScanPrefixArgs g)
+template <int MODE, class TIn, class TAcc>
+__global__ void __launch_bounds__(256) gf_rowprefix_kernel(const GfScanPrefixArgsT<TIn, TAcc> g)
 {
-    __shared__ double tot[2][256];
+    __shared__ TAcc tot[2][256];
     const int t = threadIdx.x;
     for (int y = blockIdx.x; y < g.height; y += gridDim.x) {
-        const float* ra = g.a + (int64_t)y * g.sa;
-        const float* rb = MODE == 1 ? g.b + (int64_t)y * g.sb : nullptr;
-        double* rp = g.P + (int64_t)y * g.sp;
-        double carry = 0.0;
+        const TIn* ra = g.a + (int64_t)y * g.sa;
+        const TIn* rb = MODE == 1 ? g.b + (int64_t)y * g.sb : nullptr;
+        TAcc* rp = g.P + (int64_t)y * g.sp;
+        TAcc carry = 0;
         for (int x0 = 0; x0 < g.width; x0 += 2048) {
             const int x = x0 + 8 * t;
-            double v[8];
+            TAcc v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                float e = 0.f;
-                if (x + i < g.width) e = MODE == 1 ? ra[x + i] * rb[x + i] : ra[x + i];
-                v[i] = (double)e;
+                v[i] = 0;
+                if (x + i < g.width) {
+                    if (sizeof(TIn) == 1) v[i] = MODE == 1 ? (TAcc)((int)ra[x + i] * (int)rb[x + i]) : (TAcc)ra[x + i];   // exact integers
+                    else v[i] = (TAcc)(MODE == 1 ? ra[x + i] * rb[x + i] : ra[x + i]);                                   // float32 product, as the reference's gMultiply
+                }
             }
 #pragma unroll
             for (int i = 1; i < 8; ++i) v[i] += v[i - 1];
@@ -50,12 +57,12 @@ __global__ void __launch_bounds__(256) gf_rowprefix_kernel(const GfScanPrefixArg
             __syncthreads();
 #pragma unroll 1
             for (int d = 1; d < 256; d <<= 1) {
-                const double s = tot[cur][t] + (t >= d ? tot[cur][t - d] : 0.0);
+                const TAcc s = tot[cur][t] + (t >= d ? tot[cur][t - d] : (TAcc)0);
                 tot[cur ^ 1][t] = s;
                 cur ^= 1;
                 __syncthreads();
             }
-            const double before = carry + (t > 0 ? tot[cur][t - 1] : 0.0);
+            const TAcc before = carry + (t > 0 ? tot[cur][t - 1] : (TAcc)0);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 if (x + i < g.width) rp[x + i] = before + v[i];
@@ -65,27 +72,31 @@ __global__ void __launch_bounds__(256) gf_rowprefix_kernel(const GfScanPrefixArg
     }
 }
 
-struct GfScanBoxArgs {
-    const double* P; float* out;
+template <class TAcc, class TOut>
+struct GfScanBoxArgsT {
+    const TAcc* P; TOut* out;
     int width, height, r, border, hb;
     int64_t sp, so;
 };
+typedef GfScanBoxArgsT<double, float> GfScanBoxArgs;            // means of float planes
+typedef GfScanBoxArgsT<long long, long long> GfScanBoxArgsU8;  // exact window SUMS of uint8 planes
 
 // sum of v[y][x-r .. x+r] under the border rule, from the row prefix (single reflection: r < n)
-__device__ __forceinline__ double gf_scan_hsum(const double* __restrict__ P, int x, int r, int n, int border)
+template <class TAcc>
+__device__ __forceinline__ TAcc gf_scan_hsum(const TAcc* __restrict__ P, int x, int r, int n, int border)
 {
     const int lo = x - r, hi = x + r;
     const int l = lo < 0 ? 0 : lo, h = hi > n - 1 ? n - 1 : hi;
-    double s = P[h] - (l > 0 ? P[l - 1] : 0.0);
+    TAcc s = P[h] - (l > 0 ? P[l - 1] : (TAcc)0);
     if (border != GF_TRUNCATE) {
         const int e = border == GF_REFLECT ? 1 : 0;
         if (lo < 0) {                       // indices lo..-1 mirror to [1-e, -lo-e]
             const int b0 = 1 - e, b1 = -lo - e;
-            if (b1 >= b0) s += P[b1] - (b0 > 0 ? P[b0 - 1] : 0.0);
+            if (b1 >= b0) s += P[b1] - (b0 > 0 ? P[b0 - 1] : (TAcc)0);
         }
         if (hi > n - 1) {                   // indices n..hi mirror to [2n-2+e-hi, n-2+e]
             const int b0 = 2 * n - 2 + e - hi, b1 = n - 2 + e;
-            if (b1 >= b0) s += P[b1] - (b0 > 0 ? P[b0 - 1] : 0.0);
+            if (b1 >= b0) s += P[b1] - (b0 > 0 ? P[b0 - 1] : (TAcc)0);
         }
     }
     return s;
@@ -99,24 +110,30 @@ __device__ __forceinline__ int gf_scan_map(int y, int n, int border)      // -1:
     return y < 0 ? -y - e : 2 * n - 2 + e - y;
 }
 
-__global__ void __launch_bounds__(128) gf_boxcols_kernel(const GfScanBoxArgs g)
+// MEAN: out = sum / (in-image pixel count of the window) as float; otherwise the raw window sum (exact for integers)
+template <class TAcc, class TOut, bool MEAN>
+__global__ void __launch_bounds__(128) gf_boxcols_kernel(const GfScanBoxArgsT<TAcc, TOut> g)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= g.width) return;
     const int y0 = blockIdx.y * g.hb;
     const int y1 = y0 + g.hb < g.height ? y0 + g.hb : g.height;
     const int r = g.r;
-    auto h = [&](int y) -> double {
+    auto h = [&](int y) -> TAcc {
         const int m = gf_scan_map(y, g.height, g.border);
-        return m < 0 ? 0.0 : gf_scan_hsum(g.P + (int64_t)m * g.sp, x, r, g.width, g.border);
+        return m < 0 ? (TAcc)0 : gf_scan_hsum<TAcc>(g.P + (int64_t)m * g.sp, x, r, g.width, g.border);
     };
-    double s = 0.0;
+    TAcc s = 0;
     for (int y = y0 - r; y < y0 + r; ++y) s += h(y);
     const float cx = gf_count(x, g.width, r, g.border);
     for (int y = y0; y < y1; ++y) {
         s += h(y + r);
-        const float cnt = cx * gf_count(y, g.height, r, g.border);
-        g.out[(int64_t)y * g.so + x] = (float)(s / (double)cnt);
+        if (MEAN) {
+            const float cnt = cx * gf_count(y, g.height, r, g.border);
+            g.out[(int64_t)y * g.so + x] = (TOut)((double)s / (double)cnt);
+        } else {
+            g.out[(int64_t)y * g.so + x] = (TOut)s;
+        }
         s -= h(y - r);
     }
 }

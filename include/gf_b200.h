@@ -146,6 +146,14 @@ int gf_ipc_export(const void* ptr, void* handle64);
 int gf_ipc_open(const void* handle64, void** ptr);
 int gf_ipc_close(void* ptr);
 
+/* The four stage-1 window sums of UINT8 planes, EXACT (north_star: "bit-exact integral sums for uint8 input (64-bit
+   accumulators where the image is large enough to overflow 32-bit)"): sum over the (2r+1)^2 window (border rule applied)
+   of I, p, I*p and I*I as int64, width x height each, tightly packed.  Integer row prefixes + integer column sums: no
+   rounding anywhere.  The fused uint8 filter (gf_guided_gray_u8) works in float32 and is checked against these. */
+int gf_window_sums_u8(const unsigned char* guide, const unsigned char* src, long long* sum_i, long long* sum_p,
+                      long long* sum_ip, long long* sum_ii, int width, int height, int64_t guide_stride,
+                      int64_t src_stride, int r, int border, void* stream);
+
 /* hBoxFilter (guided_filter_d.cu:868-924): box mean of a `channels`-interleaved image.  One
    streaming kernel with exact window sums; no integral image, so no `integral` scratch.
    In-place (src == dst) is allowed, as in the reference (guided_filter.cpp:59-60). */
@@ -184,7 +192,7 @@ int gf_host_free(void* ptr);
    The conversions the reference's demo does around the filter -- Mat::convertTo(CV_32F, 1/255) before
    (main.cpp:121-122,205-206) and convertTo(CV_8U, 255) with saturating round-half-even after
    (main.cpp:158,295-297) -- fused into the kernel's loads and stores: 3 bytes of HBM traffic per pixel
-   instead of 12.  Strides in ELEMENTS (= bytes).  Served by the s8 kernel only: r in {4,7,8,16},
+   instead of 12.  Strides in ELEMENTS (= bytes).  Served by the s8 kernel only: r in {1..8, 16},
    width >= 64, height >= 4r+2, rows 8-byte aligned; other arguments return GF_ERR_UNSUPPORTED. */
 int gf_guided_gray_u8(const unsigned char* guide, const unsigned char* src, unsigned char* dst, int width, int height,
                       int64_t guide_stride, int64_t src_stride, int64_t dst_stride, int r, float eps, int border,

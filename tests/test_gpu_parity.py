@@ -91,7 +91,7 @@ def test_gray_4k_r8(be, kind, border):
     assert np.abs(q - q2).max() <= 2e-6
     if border == 0:
         _, ra, rb = C.guided_gray_f32(I, p, 8, 1e-2, 0, NT, return_ab=True)
-        assert np.abs(A - ra).max() <= 2e-4 and np.abs(B - rb).max() <= 2e-4
+        assert np.abs(A - ra).max() <= TOL and np.abs(B - rb).max() <= TOL      # the 1e-4 contract, a and b included
 
 
 def test_kat_full_frame_u8(be):
@@ -124,7 +124,7 @@ def test_color_1080p_r16(be, border):
     p = np.random.default_rng(10000).random((1080, 1920), dtype=np.float32)
     q = be.guided_color(I3, p, 16, 1e-2, border)
     assert be.api.last_kernel() == ("c4_r16" if border == 0 else "generic_color")
-    ref = C.guided_color_f32(I3, p, 16, 1e-2, border, NT)
+    ref = O.guided_filter_color(I3, p, 16, 1e-2, border, np.float64)      # float64 oracle (north_star); parity unpinned (no reference golden)
     err = np.abs(q - ref).max()
     print(f"colour 1080p r=16 border={border}: max err {err:.3e}")
     assert err <= TOL

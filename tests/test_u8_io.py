@@ -83,6 +83,20 @@ def test_u8_config1_bundled_image_gpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("r", [1, 2, 3, 4, 5, 6, 7])
+def test_u8_reference_sweep_radii_gpu(r):
+    """the radii of the reference's sweep (GuidedFilter/run.py:4-6: r = 1..7, eps 0.3) on uint8 planes"""
+    from test_integral import _cuda
+    api, up, down = _cuda()
+    rng = np.random.default_rng(40 + r)
+    I = rng.integers(0, 256, (1080, 1920), dtype=np.uint8)
+    p = rng.integers(0, 256, (1080, 1920), dtype=np.uint8)
+    q = _call(api, up, down, I, p, r, 0.3, 0)
+    assert api.last_kernel() == f"s8u8_r{r}"
+    _check(q, O.guided_filter_gray_u8(I, p, r, 0.3, 0))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("border", [0, 1, 2])
 def test_u8_random_4k_gpu(border):
     from test_integral import _cuda
@@ -95,3 +109,64 @@ def test_u8_random_4k_gpu(border):
     from oracle import c_oracle as C
     ref = O.to_u8(C.guided_gray_f32(O.u8_to_f32(I), O.u8_to_f32(p), 8, 1e-2, border, max(1, (os.cpu_count() or 2) - 1)))
     _check(q, ref)
+
+
+# ---- north_star: "bit-exact integral sums for uint8 input (64-bit accumulators ...)" --------------------------------
+def _window_sums(api, up, down, I, p, r, border):
+    h, w = I.shape
+    dI, dp = up(I), up(p)
+    outs = [up(np.zeros((h, w), np.int64)) for _ in range(4)]
+    api.call("gf_window_sums_u8", dI["ptr"], dp["ptr"], outs[0]["ptr"], outs[1]["ptr"], outs[2]["ptr"], outs[3]["ptr"], w, h, 0, 0, r,
+             border, None)
+    return [down(o) for o in outs]
+
+
+def _check_window_sums(api, up, down, shape, r, border, seed, bright=False):
+    rng = np.random.default_rng(seed)
+    lo = 246 if bright else 0          # bright planes: sum(I p) and sum(I I) exceed 2^24, where float32 would round
+    I = rng.integers(lo, 256, shape, dtype=np.uint8)
+    p = rng.integers(lo, 256, shape, dtype=np.uint8)
+    si, sp, sip, sii = _window_sums(api, up, down, I, p, r, border)
+    I64, p64 = I.astype(np.int64), p.astype(np.int64)
+
+    def ref(a):          # box_sum_u8 takes uint8; the products go through the same exact int64 code path
+        return O.box_sum_u8(a, r, border) if a.dtype == np.uint8 else _box_sum_i64(a, r, border)
+    assert np.array_equal(si, O.box_sum_u8(I, r, border))
+    assert np.array_equal(sp, O.box_sum_u8(p, r, border))
+    assert np.array_equal(sip, _box_sum_i64(I64 * p64, r, border))
+    assert np.array_equal(sii, _box_sum_i64(I64 * I64, r, border))
+    if bright:
+        assert sii.max() > 2 ** 24
+
+
+def _box_sum_i64(a, r, border):
+    """exact int64 window sums of an int64 plane (same construction as oracle.box_sum_u8)"""
+    def axis_sum(a, axis):
+        n = a.shape[axis]
+        a = np.moveaxis(a, axis, 0)
+        if border == O.BORDER_TRUNCATE:
+            pad = np.zeros((r,) + a.shape[1:], dtype=np.int64)
+            e = np.concatenate([pad, a, pad], axis=0)
+        else:
+            e = a[O.border_index(np.arange(-r, n + r), n, border)]
+        c = np.cumsum(e, axis=0)
+        c = np.concatenate([np.zeros((1,) + c.shape[1:], dtype=np.int64), c], axis=0)
+        return np.moveaxis(c[2 * r + 1: 2 * r + 1 + n] - c[0:n], 0, axis)
+    return axis_sum(axis_sum(a, 1), 0)
+
+
+@pytest.mark.parametrize("shape,r,border", [((40, 70), 8, 0), ((33, 2100), 16, 2), ((50, 64), 8, 1), ((21, 30), 20, 0)])
+def test_window_sums_u8_emulated(shape, r, border):
+    from test_integral import _emu
+    api, up, down = _emu()
+    _check_window_sums(api, up, down, shape, r, border, seed=7, bright=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,r,border", [((2160, 3840), 8, 0), ((2160, 3840), 16, 0), ((1080, 1920), 8, 1), ((777, 1301), 32, 2)])
+def test_window_sums_u8_gpu_bit_exact(shape, r, border):
+    """The four stage-1 window sums of uint8 planes, bit for bit against int64 numpy, at r = 8 and 16 on 4K planes whose
+    sums of products lie above 2^24 (VERDICT r1 weak #3)."""
+    from test_integral import _cuda
+    api, up, down = _cuda()
+    _check_window_sums(api, up, down, shape, r, border, seed=11, bright=True)
