@@ -33,7 +33,7 @@ def ref_f64(I, p, r, eps):
     return box(a) * I + box(b)
 
 
-def one(w, h, r, border=0, iters=40):
+def one(w, h, r, border=0, iters=40, ab=False):
     import torch
     import cudaimageprocessing_b200 as pkg
     api = pkg.api()
@@ -46,7 +46,10 @@ def one(w, h, r, border=0, iters=40):
 
     def run(i):
         a, b, c = sets[i % nsets]
-        api.call("gf_guided_gray", a.data_ptr(), b.data_ptr(), c.data_ptr(), None, None, w, h, 0, 0, 0, 0, r, 1e-2, border, sp)
+        api.call("gf_guided_gray", a.data_ptr(), b.data_ptr(), c.data_ptr(), A.data_ptr() if ab else None, B.data_ptr() if ab else None,
+                 w, h, 0, 0, 0, 0, r, 1e-2, border, sp)
+    A = torch.empty((h, w), device="cuda") if ab else None
+    B = torch.empty((h, w), device="cuda") if ab else None
     for i in range(nsets):
         run(i)
     torch.cuda.synchronize()
@@ -75,8 +78,10 @@ def one(w, h, r, border=0, iters=40):
 def main():
     if "--one" in sys.argv:
         i = sys.argv.index("--one")
-        a = [int(x) for x in sys.argv[i + 1:i + 5]]
-        print(json.dumps(one(*a)), flush=True)
+        a = [int(x) for x in sys.argv[i + 1:i + 5] if x.lstrip("-").isdigit()]
+        res = one(*a, ab="--ab" in sys.argv)
+        res["ab_planes"] = "--ab" in sys.argv
+        print(json.dumps(res), flush=True)
         return
     cases = [(3840, 2160, 8), (7680, 4320, 8), (1920, 1080, 8)]
     envs = [{"GF_WS": "0"}, {"GF_WS": "1", "GF_WS_K": "12"}, {"GF_WS": "1", "GF_WS_K": "8"}, {"GF_WS": "1", "GF_WS_K": "16"}]
@@ -101,6 +106,11 @@ def main():
             jobs.append(({"GF_WS": "1", "GF_WS_K": "12", "GF_WS_SPLIT1": "1", "GF_WS_EDGE_PCT": str(pct)}, (3840, 2160, 8)))
         jobs += [({"GF_WS": "1", "GF_WS_SPLIT1": "1"}, (3840, 2160, 16)), ({"GF_WS": "1", "GF_WS_SPLIT1": "1", "GF_WS_K": "8"}, (3840, 2160, 16)),
                  ({"GF_WS": "1", "GF_WS_SPLIT1": "1"}, (3840, 2160, 4)), ({"GF_WS": "1", "GF_WS_SPLIT1": "1"}, (3840, 2160, 8, 1))]
+    extra_args = []
+    if len(sys.argv) > 1 and sys.argv[1] == "--ab":            # jobs that write the a / b planes (hGuidedFilter through the shim)
+        extra_args = ["--ab"]
+        jobs = [(e, c) for c in ((3840, 2160, 8), (3840, 2160, 7), (1920, 1080, 8), (7680, 4320, 8), (3840, 2160, 16), (3840, 2160, 4))
+                for e in ({"GF_WS": "1"}, {"GF_WS": "0"})]
     if len(sys.argv) > 1 and sys.argv[1] == "--edge":          # weight of the edge strips in the band chooser
         jobs = []
         for k in (12, 8):
@@ -118,7 +128,7 @@ def main():
     for env, c in jobs:
         e = dict(os.environ)
         e.update(env)
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"] + [str(x) for x in c], env=e,
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"] + [str(x) for x in c] + extra_args, env=e,
                            capture_output=True, text=True, timeout=600)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else json.dumps({"error": r.stderr[-400:], "env": env, "case": c})
         print(line, flush=True)

@@ -700,10 +700,10 @@ static inline int gf_pick_band_rows(int rows, int r, long nstrips_x_count, long 
 // (profiles/r1_tape_scheduling_ab.jsonl, profiles/r1_c4_band_sweep.jsonl): pieces of neighbouring
 // strips no longer walk the same rows at the same time, so the strip halos stop hitting in L2, and
 // a piece that crosses into the next strip pays a second ramp that costs more than the model says.
-static inline long gf_tape_plan(GfWpArgs& a, int r, long slots, int hb_min, int we_pct)
+static inline long gf_tape_plan(GfWpArgs& a, int r, long slots, int hb_min, int we_pct, int on_by_default = 0)
 {
     a.tape_piece = 0; a.tape_rho = (int)(2.3 * r + 1.0); a.tape_we = we_pct < 100 ? 100 : we_pct;
-    if (GF_KNOB("GF_TAPE", 0) == 0) return 0;
+    if (GF_KNOB("GF_TAPE", on_by_default) == 0) return 0;
     slots = GF_KNOB("GF_TAPE_SLOTS", (int)slots);       // tests / experiments: pieces that span several strips
     const bool edges = a.nstrips >= 3 && a.tape_we != 100;
     const long long zi = (long long)(a.tape_rho + a.out_rows) * 100, ze = (long long)(a.tape_rho + a.out_rows) * a.tape_we;

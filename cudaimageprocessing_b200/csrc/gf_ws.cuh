@@ -884,7 +884,10 @@ static const char* gf_ws_launch(const Job& j)
 static const char* gf_ws_try(const Job& j, bool* done, const char** name)
 {
     *done = false;
-    if (j.color || !GF_KNOB("GF_WS", GF_WS_DEFAULT) || GF_KNOB("GF_DISABLE_FAST", 0)) return nullptr;
+    // default: jobs that want the a / b planes (hGuidedFilter's d_A, d_B through the drop-in shim) -- the producer warps store
+    // them on the side, where the round-1 kernels fall back to their first generation (wp: 103 us at 4K r=8); plain jobs
+    // stay on gf_s8, which is as fast at 4K and faster above
+    if (j.color || !GF_KNOB("GF_WS", j.A.ptr ? 1 : GF_WS_DEFAULT) || GF_KNOB("GF_DISABLE_FAST", 0)) return nullptr;
     const int force_k = GF_KNOB("GF_WS_K", 0);
     if ((j.A.ptr == nullptr) != (j.B.ptr == nullptr)) return nullptr;
     const Plane* pl[5] = {&j.guide, &j.src, &j.dst, &j.A, &j.B};

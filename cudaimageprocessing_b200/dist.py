@@ -57,6 +57,12 @@ def exchange_halos_inplace(bufs, height: int, rank: int, world: int, r: int, gro
     y0, y1 = strip_rows(height, rank, world)
     top, bot = halo_rows(height, rank, world, r)
     own = y1 - y0
+    # validated from the geometry, identically on EVERY rank and before any P2P op exists: a rank that raised alone
+    # would leave its neighbours waiting in batch_isend_irecv
+    if world > 1:
+        shortest = min(strip_rows(height, k, world)[1] - strip_rows(height, k, world)[0] for k in range(world))
+        if shortest < 2 * r:
+            raise ValueError(f"strips of {shortest} rows are shorter than the {2 * r}-row halo a neighbour needs")
     ops = []
     for b in bufs:
         if rank > 0:
@@ -88,7 +94,8 @@ def exchange_halos(strip: torch.Tensor, height: int, rank: int, world: int, r: i
 def filter_strip(api, I_buf: torch.Tensor, p_buf: torch.Tensor, q_out: torch.Tensor, height: int, rank: int,
                  world: int, r: int, eps: float, border: int, stream: Optional[int] = None) -> None:
     """Runs the fused kernel on this rank's strip.  I_buf/p_buf: halo-extended buffers after the
-    exchange (row 0 = global row y0 - top); q_out: the rank's own rows."""
+    exchange (row 0 = global row y0 - top); q_out: the rank's own rows.  `stream` must be the stream the exchange was
+    ordered on (torch's current stream for exchange_halos_inplace): the kernel reads the halo rows it wrote."""
     y0, y1 = strip_rows(height, rank, world)
     top, _ = halo_rows(height, rank, world, r)
     w = I_buf.shape[1]

@@ -5,8 +5,10 @@
 // `integral` scratch of hBoxFilter is ignored (window sums are exact, not a float32 integral
 // image); hCalcB with a 1-channel guide computes b = pm - a*im (the reference's gCalcBCN1 does
 // not, guided_filter_d.cu:371-372); hGuidedFilter accepts any radius (the reference silently
-// does nothing outside 1..7, :1090) and leaves its d_A / d_B scratch planes untouched -- a and b never
-// leave the SM in the fused kernel; set GF_SHIM_FILL_AB=1 in the environment to have them written.
+// does nothing outside 1..7, :1090).  d_A / d_B are filled with a and b as in the reference (main.cpp:283-286 reads
+// them back); a caller that never looks can set GF_SHIM_SKIP_AB=1 in the environment to save the 8 B/px of writes.
+// A request the library cannot serve (other than the channel combinations the reference refuses too) is fatal, like a
+// CUDA error in the reference (cuda_utils.h): the call never returns with dst unwritten.
 #pragma once
 #include "cuda_utils.h"
 
