@@ -36,16 +36,41 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile_and_link(out: str, defines: list[str]) -> tuple[int, str]:
+    """Every .cu under csrc/ is one translation unit: compiled to an object file in parallel, then linked."""
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: libgf_b200.so cannot be built (there is no CPU fallback)")
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-I", os.path.join(ROOT, "include"), "-I", CSRC] + list(defines)
+    if os.path.exists(os.path.join(CSRC, "gf_fast.cuh")):
+        flags.append("-DGF_HAVE_FAST")
+    log = []
+    with tempfile.TemporaryDirectory(prefix="gfbuild_") as tmp:
+        def one(src):
+            obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
+            res = subprocess.run([nvcc] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+            return res.returncode, res.stdout + res.stderr, obj
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+            results = list(ex.map(one, _sources()))
+        for rc, text, _ in results:
+            log.append(text)
+            if rc != 0:
+                return rc, "".join(log)
+        res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + [o for _, _, o in results],
+                             capture_output=True, text=True)
+        log.append(res.stdout + res.stderr)
+        return res.returncode, "".join(log)
+
+
 def build_variant(name: str, defines: list[str]) -> str:
     """Developer tool: a differently configured build (e.g. -DGF_S8_NEWTON=0) next to the product
     library, for A/B timing through GF_LIB_PATH (bench_tools/ab.py).  Never loaded by default."""
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     out = os.path.join(PKG, name)
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-DGF_HAVE_FAST"] + \
-          list(defines) + ["-o", out] + _sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+    rc, text = _compile_and_link(out, defines)
+    if rc != 0:
+        sys.stderr.write(text)
         raise RuntimeError("nvcc failed building " + name)
     return out
 
@@ -53,20 +78,13 @@ def build_variant(name: str, defines: list[str]) -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        raise RuntimeError("nvcc not found: libgf_b200.so cannot be built (there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-DGF_HAVE_FAST",
-                                 "-o", LIB] + _sources()
-    if not os.path.exists(os.path.join(CSRC, "gf_fast.cuh")):
-        cmd.remove("-DGF_HAVE_FAST")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    rc, text = _compile_and_link(LIB, [])
+    if verbose or rc != 0:
+        sys.stderr.write(text)
+    if rc != 0:
         raise RuntimeError("nvcc failed building libgf_b200.so")
     with open(os.path.join(PKG, "build_ptxas.log"), "w") as f:
-        f.write(res.stdout + res.stderr)
+        f.write(text)
     return LIB
 
 

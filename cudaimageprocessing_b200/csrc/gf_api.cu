@@ -22,9 +22,14 @@
 #ifdef GF_HAVE_FAST
 #include "gf_fast.cuh"
 #include "gf_wp.cuh"
-#include "gf_s8.cuh"
-#include "gf_ws.cuh"
-#include "gf_c4.cuh"
+// the three big kernel families live in their own translation units (gf_tu_s8.cu, gf_tu_ws.cu, gf_tu_c4.cu) so that the
+// library builds in parallel
+const char* gf_s8_try_x(const Job& j, bool* done, const char** name, bool u8);
+const char* gf_ws_try_x(const Job& j, bool* done, const char** name);
+const char* gf_c4_try_x(const Job& j, bool* done, const char** name);
+static inline const char* gf_s8_try(const Job& j, bool* done, const char** name, bool u8 = false) { return gf_s8_try_x(j, done, name, u8); }
+static inline const char* gf_ws_try(const Job& j, bool* done, const char** name) { return gf_ws_try_x(j, done, name); }
+static inline const char* gf_c4_try(const Job& j, bool* done, const char** name) { return gf_c4_try_x(j, done, name); }
 #endif
 
 namespace {

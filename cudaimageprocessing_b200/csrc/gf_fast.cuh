@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NW * 32) gf_fast_gray_kernel(const GfFastArgs 
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-#ifndef GF_NO_HOST   // (stand-alone SASS builds of one kernel define GF_NO_HOST)
+#if !defined(GF_NO_HOST) && !defined(GF_FAST_NO_TRY)   // (stand-alone SASS builds define GF_NO_HOST; other translation units GF_FAST_NO_TRY)
 template <int R, int NW>
 struct GfFastLaunch {
     static const char* go(const Job& j, const char** name)

@@ -716,6 +716,7 @@ static inline long gf_tape_plan(GfWpArgs& a, int r, long slots, int hb_min, int 
     return (long)((total + a.tape_piece - 1) / a.tape_piece);
 }
 
+#ifndef GF_S8_NO_TRY     // (translation units that only need the helpers above: gf_tu_ws.cu, gf_tu_c4.cu, gf_api.cu)
 template <int R, class T = float>
 static const char* gf_s8_launch(const Job& j)
 {
@@ -829,4 +830,5 @@ static const char* gf_s8_try(const Job& j, bool* done, const char** name, bool u
     default: return nullptr;
     }
 }
+#endif  // GF_S8_NO_TRY
 #endif  // GF_NO_HOST

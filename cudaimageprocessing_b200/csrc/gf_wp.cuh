@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(GfWpGeom<R, K>::WARPS * 32, MINB) gf_wp_gray_k
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-#ifndef GF_NO_HOST   // (stand-alone SASS builds of one kernel define GF_NO_HOST)
+#if !defined(GF_NO_HOST) && !defined(GF_WP_NO_TRY)   // (stand-alone SASS builds define GF_NO_HOST; other translation units GF_WP_NO_TRY)
 template <int R, int K>
 static const char* gf_wp_launch(const Job& j)
 {

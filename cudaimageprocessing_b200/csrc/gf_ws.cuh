@@ -763,7 +763,8 @@ __global__ void __launch_bounds__((SPLIT ? 96 : 64) * NS, 1) gf_ws_gray_kernel(c
     const int y0 = a.out_y0 + band * hbw;
     const int y1 = y0 + hbw < a.out_y0 + a.out_rows ? y0 + hbw : a.out_y0 + a.out_rows;
     if (threadIdx.x < 2 * NS) ctrl[threadIdx.x] = 0;
-    if (threadIdx.x < NS * G::NBAR) gf_ws_bar_init(reinterpret_cast<unsigned long long*>(const_cast<int*>(ctrl) + 16) + threadIdx.x);
+    for (int i = threadIdx.x; i < NS * G::NBAR; i += blockDim.x)          // (2-stream CTAs have fewer threads than barriers)
+        gf_ws_bar_init(reinterpret_cast<unsigned long long*>(const_cast<int*>(ctrl) + 16) + i);
     __syncthreads();
     GfWsPlan<NS> pl;
     gf_ws_plan<R, NS>(y0, y1, pl);
@@ -806,6 +807,13 @@ __global__ void __launch_bounds__((SPLIT ? 96 : 64) * NS, 1) gf_ws_gray_kernel(c
 // Producer split over two warps (option GF_WS_SPLIT1 overrides)
 #ifndef GF_WS_SPLIT1_DEFAULT
 #define GF_WS_SPLIT1_DEFAULT 0
+#endif
+#ifndef GF_WS_WITH_SPLIT1
+#ifdef GF_CPU_EMU
+#define GF_WS_WITH_SPLIT1 1
+#else
+#define GF_WS_WITH_SPLIT1 0
+#endif
 #endif
 #ifndef GF_WS_MAX_SUB
 #define GF_WS_MAX_SUB 512
@@ -866,7 +874,13 @@ static const char* gf_ws_launch(const Job& j)
     }
     a.hb = bd.hb; a.nbands = bd.nbands; a.hb_e = bd.hb_e; a.nbands_e = bd.nbands_e;
     const long items = (a.nbands_e > 0 ? 2L * a.nbands_e + (long)(a.nstrips - 2) * a.nbands : (long)a.nstrips * a.nbands) * j.count;
+    // The split-producer kernels (measured 20-90 % slower) are compiled only into the emulator
+    // build (their hand-off logic stays under test) and into -DGF_WS_WITH_SPLIT1=1 experiment builds.
+#if GF_WS_WITH_SPLIT1
     const bool split = GF_KNOB("GF_WS_SPLIT1", GF_WS_SPLIT1_DEFAULT) != 0;
+#else
+    const bool split = false;
+#endif
     dim3 grid((unsigned)items), block((split ? 96 : 64) * NS);
     const char* e;
 #define GF_WS_GO(TR, SP)                                                        \
@@ -875,8 +889,12 @@ static const char* gf_ws_launch(const Job& j)
         if ((e = gf_rt_set_smem(kf, G::smem_bytes))) return e;                  \
         GF_LAUNCH(kf, grid, block, G::smem_bytes, j.stream, a);                 \
     } while (0)
+#if GF_WS_WITH_SPLIT1
     if (j.border == GF_TRUNCATE) { if (split) GF_WS_GO(true, true); else GF_WS_GO(true, false); }
     else { if (split) GF_WS_GO(false, true); else GF_WS_GO(false, false); }
+#else
+    if (j.border == GF_TRUNCATE) GF_WS_GO(true, false); else GF_WS_GO(false, false);
+#endif
 #undef GF_WS_GO
     return gf_rt_launch_error();
 }
@@ -918,7 +936,6 @@ static const char* gf_ws_try(const Job& j, bool* done, const char** name)
     GF_WS_CASE(7, 12, 4, "ws_r7_k12")
     GF_WS_CASE(4, 8, 6, "ws_r4_k8")
     GF_WS_CASE(16, 12, 2, "ws_r16_k12")
-    GF_WS_CASE(16, 8, 3, "ws_r16_k8")
 #endif
 #undef GF_WS_CASE
     return nullptr;

@@ -16,12 +16,20 @@ def build_emu(force: bool = False) -> str:
            [os.path.join(ROOT, "include", "gf_b200.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
-    cmd = ["/usr/bin/g++", "-O1", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-DGF_CPU_EMU",
-           "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           "-x", "c++", os.path.join(CSRC, "gf_api.cu"), os.path.join(HERE, "cuda_emu.cpp"), "-o", LIB]
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    flags = ["-O1", "-std=c++17", "-fopenmp", "-fPIC", "-DGF_CPU_EMU", "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if os.path.exists(os.path.join(CSRC, "gf_fast.cuh")):
-        cmd.insert(1, "-DGF_HAVE_FAST")
-    subprocess.check_call(cmd)
+        flags.insert(0, "-DGF_HAVE_FAST")
+    units = [os.path.join(CSRC, f) for f in ("gf_api.cu", "gf_tu_s8.cu", "gf_tu_ws.cu", "gf_tu_c4.cu")] + [os.path.join(HERE, "cuda_emu.cpp")]
+    with tempfile.TemporaryDirectory(prefix="gfemu_") as tmp:
+        def one(src):
+            obj = os.path.join(tmp, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+            subprocess.check_call(["/usr/bin/g++"] + flags + ["-x", "c++", "-c", src, "-o", obj])
+            return obj
+        with ThreadPoolExecutor(max_workers=5) as ex:          # one translation unit per kernel family, in parallel
+            objs = list(ex.map(one, units))
+        subprocess.check_call(["/usr/bin/g++", "-shared", "-fopenmp", "-o", LIB] + objs)
     return LIB
 
 
