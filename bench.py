@@ -381,7 +381,8 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            line["roofline"]["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            tj = json.load(open(prof))
+            line["roofline"]["traffic"] = tj.get("per_kernel", {}).get(kernel_name, {}).get("dram_bytes_per_launch", tj.get("dram_bytes_per_launch"))
         except Exception:
             pass
     if world == 1:

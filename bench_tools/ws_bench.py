@@ -117,6 +117,14 @@ def main():
             for pct in (135, 160, 185, 210, 240):
                 for c in ((3840, 2160, 8), (7680, 4320, 8)):
                     jobs.append(({"GF_WS": "1", "GF_WS_K": str(k), "GF_WS_EDGE_PCT": str(pct)}, c))
+    if len(sys.argv) > 1 and sys.argv[1] == "--tune":          # ws_bench.py --tune [lib.so ...]: edge weight x build variant, K = 12
+        libs = sys.argv[2:] or ["libgf_b200.so"]
+        jobs = []
+        for lib in libs:
+            path = os.path.join(ROOT, "cudaimageprocessing_b200", lib)
+            for pct in (135, 150, 165, 180):
+                for c in ((3840, 2160, 8), (7680, 4320, 8)):
+                    jobs.append(({"GF_LIB_PATH": path, "GF_WS": "1", "GF_WS_K": "12", "GF_WS_EDGE_PCT": str(pct)}, c))
     if len(sys.argv) > 1 and sys.argv[1] == "--variants":      # differently compiled builds: ws_bench.py --variants libA.so libB.so ...
         libs = sys.argv[2:]
         jobs = []

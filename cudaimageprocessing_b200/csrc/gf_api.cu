@@ -669,6 +669,40 @@ int gf_guided_gray_strip(const float* guide, const float* src, float* dst, int w
     return run_jobs(&j, 1);
 }
 
+// Copies up to four row blocks (the 2r halo rows of two planes from two neighbour ranks) from peer-mapped memory into
+// the local strip buffers: blockIdx.y = region, grid-stride over its 16-byte (or 4-byte) elements.
+struct GfHaloPullArgs {
+    float* dst[4]; const float* src[4];
+    int64_t dstride[4], sstride[4];
+    int rows[4];
+    int width, vec4;
+};
+#ifndef GF_CPU_EMU
+__global__ void __launch_bounds__(256) gf_halo_pull_kernel(const GfHaloPullArgs g)
+{
+    const int rg = blockIdx.y;
+    const int rows = g.rows[rg];
+    if (rows <= 0) return;
+    float* d = g.dst[rg];
+    const float* s = g.src[rg];
+    const int64_t ds = g.dstride[rg], ss = g.sstride[rg];
+    if (g.vec4) {
+        const int w4 = g.width >> 2;
+        const int64_t n = (int64_t)rows * w4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            const int y = (int)(i / w4), x = (int)(i - (int64_t)y * w4);
+            reinterpret_cast<float4*>(d + y * ds)[x] = reinterpret_cast<const float4*>(s + y * ss)[x];
+        }
+    } else {
+        const int64_t n = (int64_t)rows * g.width;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            const int y = (int)(i / g.width), x = (int)(i - (int64_t)y * g.width);
+            d[y * ds + x] = s[y * ss + x];
+        }
+    }
+}
+#endif
+
 // ---- row strips with the halo exchange inside the call (gf_run_strips) ------------------------
 static void strip_halo_rows(int global_height, int y0, int rows, int r, int* top, int* bot)
 {
@@ -700,59 +734,45 @@ int gf_run_strips(float* guide_buf, float* src_buf, float* dst, int width, int g
     if ((up && top > 0 && up->rows < top) || (down && bot > 0 && down->rows < bot))
         return fail(GF_ERR_INVALID, "gf_run_strips: a neighbour strip is shorter than the %d-row halo it must supply", 2 * r);
 #ifndef GF_CPU_EMU
-    // The four halo copies (2 planes x 2 neighbours) are independent: they go out on four side streams (one copy engine
-    // each) forked from `stream` and joined before the kernel -- 0.06 ms when issued back to back on one stream at 8 GPUs,
-    // the difference between 6.8x and 7x on BASELINE configs[4].
-    struct StripPipe { cudaStream_t st[4]; cudaEvent_t fork, join[4]; bool init; };
-    static StripPipe pipes[64];
-    static std::mutex pipes_mu;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(GF_ERR_CUDA, "gf_run_strips: cudaGetDevice");
-    StripPipe& sp = pipes[dev];
-    std::lock_guard<std::mutex> lock(pipes_mu);      // the fork / join events are shared by every caller on this device: enqueue atomically
-    if (!sp.init) {
-        cudaError_t e0 = cudaEventCreateWithFlags(&sp.fork, cudaEventDisableTiming);
-        for (int i = 0; i < 4 && e0 == cudaSuccess; ++i) {
-            e0 = cudaStreamCreateWithFlags(&sp.st[i], cudaStreamNonBlocking);
-            if (e0 == cudaSuccess) e0 = cudaEventCreateWithFlags(&sp.join[i], cudaEventDisableTiming);
-        }
-        if (e0 != cudaSuccess) return fail(GF_ERR_CUDA, "gf_run_strips: side streams: %s", cudaGetErrorString(e0));
-        sp.init = true;
-    }
-    const size_t row_bytes = (size_t)width * sizeof(float);
-    int lane = 0;
-    cudaError_t e = cudaSuccess;
-    bool forked = false;
-    auto pull = [&](float* dst_rows, int64_t dstride, const float* peer, int64_t pstride, int first_row, int n) -> cudaError_t {
-        if (n <= 0) return cudaSuccess;
-        cudaError_t r = cudaSuccess;
-        if (!forked) {
-            r = cudaEventRecord(sp.fork, (cudaStream_t)stream);
-            forked = true;
-        }
+    // ONE small kernel pulls all four halo regions (2 planes x 2 neighbours) straight out of the peers' memory with
+    // 16-byte loads over NVLink.  Measured at 8 GPUs (32768^2, r=16, 16 MiB of halos per rank): four cudaMemcpy2DAsync
+    // cost 0.061 ms back to back on the stream and 0.063 ms on four side streams (copy-engine set-up and cross-stream
+    // events, not bandwidth) -- the difference between 6.8x and 7x on BASELINE configs[4].
+    GfHaloPullArgs pa;
+    int nreg = 0;
+    auto add = [&](float* dst_rows, int64_t dstride, const float* peer, int64_t pstride, int first_row, int n) {
+        if (n <= 0) return;
         const int64_t ps = pstride > 0 ? pstride : width;
-        cudaStream_t side = sp.st[lane];
-        if (r == cudaSuccess) r = cudaStreamWaitEvent(side, sp.fork, 0);
-        if (r == cudaSuccess)
-            r = cudaMemcpy2DAsync(dst_rows, (size_t)dstride * sizeof(float), peer + (int64_t)first_row * ps, (size_t)ps * sizeof(float),
-                                  row_bytes, (size_t)n, cudaMemcpyDefault, side);
-        if (r == cudaSuccess) r = cudaEventRecord(sp.join[lane], side);
-        if (r == cudaSuccess) r = cudaStreamWaitEvent((cudaStream_t)stream, sp.join[lane], 0);
-        ++lane;
-        return r;
+        pa.dst[nreg] = dst_rows; pa.src[nreg] = peer + (int64_t)first_row * ps; pa.dstride[nreg] = dstride; pa.sstride[nreg] = ps; pa.rows[nreg] = n;
+        ++nreg;
     };
     if (up && top > 0) {           // the LAST `top` own rows of the strip above -> my first `top` rows
         if (!up->guide || !up->src) return fail(GF_ERR_INVALID, "gf_run_strips: null peer pointer (up)");
         const int first = up->top + up->rows - top;
-        if ((e = pull(guide_buf, gs, up->guide, up->guide_stride, first, top)) == cudaSuccess) e = pull(src_buf, ss, up->src, up->src_stride, first, top);
+        add(guide_buf, gs, up->guide, up->guide_stride, first, top);
+        add(src_buf, ss, up->src, up->src_stride, first, top);
     }
-    if (e == cudaSuccess && down && bot > 0) {    // the FIRST `bot` own rows of the strip below -> my last `bot` rows
+    if (down && bot > 0) {         // the FIRST `bot` own rows of the strip below -> my last `bot` rows
         if (!down->guide || !down->src) return fail(GF_ERR_INVALID, "gf_run_strips: null peer pointer (down)");
         const int64_t off = (int64_t)(top + rows);
-        if ((e = pull(guide_buf + off * gs, gs, down->guide, down->guide_stride, down->top, bot)) == cudaSuccess)
-            e = pull(src_buf + off * ss, ss, down->src, down->src_stride, down->top, bot);
+        add(guide_buf + off * gs, gs, down->guide, down->guide_stride, down->top, bot);
+        add(src_buf + off * ss, ss, down->src, down->src_stride, down->top, bot);
     }
-    if (e != cudaSuccess) return fail(GF_ERR_CUDA, "gf_run_strips: peer copy of the halo rows: %s", cudaGetErrorString(e));
+    if (nreg > 0) {
+        for (int i = nreg; i < 4; ++i) { pa.dst[i] = nullptr; pa.src[i] = nullptr; pa.dstride[i] = pa.sstride[i] = 0; pa.rows[i] = 0; }
+        pa.width = width;
+        bool v4 = (width & 3) == 0;
+        for (int i = 0; i < nreg; ++i)
+            v4 = v4 && !((uintptr_t)pa.dst[i] & 15) && !((uintptr_t)pa.src[i] & 15) && !(pa.dstride[i] & 3) && !(pa.sstride[i] & 3);
+        pa.vec4 = v4 ? 1 : 0;
+        int sms = 148, mj = 0, mn = 0;
+        gf_rt_device_info(&sms, &mj, &mn);
+        dim3 grid(sms, nreg), block(256);
+        auto k = gf_halo_pull_kernel;
+        GF_LAUNCH(k, grid, block, 0, stream, pa);
+        if (const char* le = gf_rt_launch_error()) return fail(GF_ERR_CUDA, "gf_run_strips: halo pull kernel: %s", le);
+        g_launches++;
+    }
 #else
     auto pull = [&](float* dst_rows, int64_t dstride, const float* peer, int64_t pstride, int first_row, int n) {
         const int64_t ps = pstride > 0 ? pstride : width;

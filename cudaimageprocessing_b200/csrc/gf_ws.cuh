@@ -35,7 +35,7 @@
 #define GF_WS_NEWTON 1       // one Newton step after MUFU.RCP in the a/b solve
 #endif
 #ifndef GF_WS_SPLIT
-#define GF_WS_SPLIT 1        // prefix / suffix chains of the window sums in two halves
+#define GF_WS_SPLIT 0        // prefix / suffix chains of the window sums in two halves: measured 1-2 % SLOWER (r2_ws_variants.jsonl)
 #endif
 #ifndef GF_WS_PF
 #define GF_WS_PF 0           // rows ahead for an L2 prefetch hint of the entering row; measured 4-6 % SLOWER at 4K/8K
@@ -374,6 +374,31 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
             }
         }
     };
+    // the K columns of this lane from a row pointer that already points at the lane's first column
+    auto ld_vec = [&](const float* rp, float (&v)[K]) {
+            if (EM == 1 || EM == 2) {      // edge strip: groups outside the image are not read (their sums are mirrored in)
+#pragma unroll
+                for (int c = 0; c < K / 4; ++c) {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cmask >> c & 1) t = *reinterpret_cast<const float4*>(rp + 4 * c);
+                    v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+                }
+            } else if (K % 8 == 0) {       // one 32-byte access per 8 columns: lane stride = access size, fully coalesced
+#pragma unroll
+                for (int c = 0; c < K / 8; ++c) {
+                    float2 t[4];
+                    gf_ld8(rp + 8 * c, t);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { v[8 * c + 2 * i] = t[i].x; v[8 * c + 2 * i + 1] = t[i].y; }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < K / 4; ++c) {
+                    const float4 t = *reinterpret_cast<const float4*>(rp + 4 * c);
+                    v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+                }
+            }
+    };
     auto ld_row = [&](const float* plane, const float* planex, int64_t stride, int rr, float (&v)[K]) {
         if (TRUNC && rr < 0) {
 #pragma unroll
@@ -453,6 +478,12 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
 #pragma unroll
         for (int j = 0; j < K; ++j) oI[j] = oP[j] = 0.f;
     }
+    // running pointers (simple streams): the rows of iteration m0 -- entering row m0+R, leaving row m0-R-1 (not used)
+    const int64_t stepI = (int64_t)st.d * a.gs, stepP = (int64_t)st.d * a.ss;
+    const float* pnI = gIx + (int64_t)(rbase + st.d * (st.m0 + R)) * a.gs;
+    const float* pnP = gPx + (int64_t)(rbase + st.d * (st.m0 + R)) * a.ss;
+    const float* poI = gIx + (int64_t)(rbase + st.d * (st.m0 - R - 1)) * a.gs;
+    const float* poP = gPx + (int64_t)(rbase + st.d * (st.m0 - R - 1)) * a.ss;
     float cx[K];                     // TRUNCATE: in-image columns of the window of each column
     if (TRUNC) {
 #pragma unroll
@@ -508,11 +539,19 @@ __device__ __forceinline__ void gf_ws_stage1(const GfWsArgs& a, const GfWsPlan<N
         if (ROLE != 1 && m + GF_WS_PF + 1 < st.m1) prefetch_row(m + 1 + R + GF_WS_PF);
         const int cons_seen = ROLE != 1 ? gf_ws_ld_acq(cons_own) : 0;      // read early, needed just before the ring store
         if (m + 1 < st.m1) {
-            const int rn = row_of(m + 1 + R), ro = row_of(m - R);
-            ld_row(gI, gIx, a.gs, rn, nI);
-            ld_row(gP, gPx, a.ss, rn, nP);
-            ld_row(gI, gIx, a.gs, ro, oI);
-            ld_row(gP, gPx, a.ss, ro, oP);
+            if (EM != 3 && simple) {       // rows never leave the image: four running row pointers, no per-row address arithmetic
+                pnI += stepI; pnP += stepP; poI += stepI; poP += stepP;
+                ld_vec(pnI, nI);
+                ld_vec(pnP, nP);
+                ld_vec(poI, oI);
+                ld_vec(poP, oP);
+            } else {
+                const int rn = row_of(m + 1 + R), ro = row_of(m - R);
+                ld_row(gI, gIx, a.gs, rn, nI);
+                ld_row(gP, gPx, a.ss, rn, nP);
+                ld_row(gI, gIx, a.gs, ro, oI);
+                ld_row(gP, gPx, a.ss, ro, oP);
+            }
         }
         // ---- horizontal: window sums of the two quantity pairs ----
         const int idx = m - st.m0;
@@ -662,9 +701,12 @@ __device__ __forceinline__ void gf_ws_stage2(const GfWsArgs& a, const GfWsPlan<N
         prod = ctrl + 2 * t;
         bar = bars + t * G::NBAR;
     };
-    auto ld_guide = [&](int i, float (&g)[K]) {
-        const int y = st.ys + st.d * i;
-        const float* rp = gI + (int64_t)(y - a.buf_y0) * a.gs;
+    const int64_t stepG = (int64_t)st.d * a.gs, stepQ = (int64_t)st.d * a.ds;
+    const float* gp = gI + (int64_t)(st.ys - a.buf_y0) * a.gs - stepG;      // advanced by one row per ld_guide call (rows i = 0, 1, ..)
+    float* qrow = gQ + (int64_t)(st.ys - a.out_y0) * a.ds - stepQ;
+    auto ld_guide = [&](int, float (&g)[K]) {
+        gp += stepG;
+        const float* rp = gp;
 #pragma unroll
         for (int c = 0; c < K / 4; ++c) {
             float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -728,8 +770,8 @@ __device__ __forceinline__ void gf_ws_stage2(const GfWsArgs& a, const GfWsPlan<N
             }
         }
         {
-            const int y = st.ys + st.d * i;
-            float* qp = gQ + (int64_t)(y - a.out_y0) * a.ds;
+            qrow += stepQ;
+            float* qp = qrow;
 #pragma unroll
             for (int c = 0; c < K / 4; ++c)
                 if (omask >> c & 1) *reinterpret_cast<float4*>(qp + 4 * c) = make_float4(q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);

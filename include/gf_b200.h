@@ -120,8 +120,8 @@ int gf_guided_gray_strip(const float* guide, const float* src, float* dst, int w
    `up` / `down` describe the strip buffers of the rank above / below AS SEEN FROM THIS DEVICE: device pointers to THEIR
    buffer row 0 (the same process with peer access enabled, or another process's gf_device_alloc'ed buffer opened with
    gf_ipc_open), their strides, their own `top` and `rows`.  The call PULLS the halo rows it needs straight out of the
-   neighbours' own rows -- four strided peer copies on `stream` (copy engines over NVLink: no SM time, no NCCL,
-   no staging) -- and launches the strip kernel behind them on the same stream.
+   neighbours' own rows -- one small kernel on `stream` that reads the peers' memory with 16-byte loads over
+   NVLink (no NCCL, no staging, no copy-engine set-up) -- and launches the strip kernel behind it on the same stream.
    up == NULL / down == NULL: that halo (if the layout has one) is already in the buffer, e.g. after an
    ncclSend/ncclRecv exchange done by the caller (dist.exchange_halos_inplace).
    Ordering across ranks is the caller's: the neighbours' own rows must be complete before the call and unchanged

@@ -258,6 +258,21 @@ def test_color_c4_radii_and_batch(be, r):
         assert np.abs(q[k] - C.guided_color_f32(I[k], p[k], r, 1e-2, 0, NT)).max() <= TOL
 
 
+def test_color_batch_tape_window(be, knob):
+    """16 frames of 1080p colour = 33 Mpx: inside the window where the equal-cost "tape" split is on by default for the
+    colour kernel (BASELINE configs[2] at 8 GPUs is 32 frames per rank).  Same result as the uniform split, right answer."""
+    rng = np.random.default_rng(12)
+    I = rng.random((16, 1080, 1920, 3), dtype=np.float32)
+    p = rng.random((16, 1080, 1920), dtype=np.float32)
+    q = be.batch(I, p, 16, 1e-2, 0)
+    assert be.api.last_kernel() == "c4_r16"
+    for k in (0, 7, 15):
+        assert np.abs(q[k] - C.guided_color_f32(I[k], p[k], 16, 1e-2, 0, NT)).max() <= TOL
+    knob(be, "GF_TAPE", 0)
+    q0 = be.batch(I, p, 16, 1e-2, 0)
+    assert np.abs(q - q0).max() <= 1e-5          # (band starts differ, so the running sums are re-seeded at other rows)
+
+
 def test_color_small_and_3ch_src(be):
     rng = np.random.default_rng(4)
     I3 = rng.random((70, 95, 3), dtype=np.float32)
