@@ -125,6 +125,13 @@ def main():
             for pct in (135, 150, 165, 180):
                 for c in ((3840, 2160, 8), (7680, 4320, 8)):
                     jobs.append(({"GF_LIB_PATH": path, "GF_WS": "1", "GF_WS_K": "12", "GF_WS_EDGE_PCT": str(pct)}, c))
+    if len(sys.argv) > 1 and sys.argv[1] == "--pen":           # rows the outer streams get fewer / edge weight
+        jobs = []
+        for pen in (1, 3, 5, 7):
+            for pct in (115, 135):
+                for c in ((3840, 2160, 8), (7680, 4320, 8)):
+                    jobs.append(({"GF_WS": "1", "GF_WS_K": "12", "GF_WS_PEN": str(pen), "GF_WS_EDGE_PCT": str(pct)}, c))
+        jobs += [({"GF_WS": "1", "GF_WS_K": "12", "GF_WS_PEN": str(pen)}, (1920, 1080, 8)) for pen in (1, 3, 5, 7)]
     if len(sys.argv) > 1 and sys.argv[1] == "--variants":      # differently compiled builds: ws_bench.py --variants libA.so libB.so ...
         libs = sys.argv[2:]
         jobs = []

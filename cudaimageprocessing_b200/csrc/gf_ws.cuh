@@ -53,6 +53,8 @@ struct GfWsArgs {
     int nstrips, nbands, hb, count;
     int nbands_e, hb_e;              // band count / height of the first and last strip (0: same as the others)
     float eps;
+    int pen;                         // rows the two outer streams of a CTA get fewer than the inner ones (gf_ws_plan)
+    long long* dbg;                  // -DGF_WS_TIMING experiment builds only: per-warp (start, end) clocks; nullptr in the product
 };
 
 template <int R, int K, int NS>
@@ -275,12 +277,12 @@ struct GfWsPlan {
 };
 
 template <int R, int NS>
-__host__ __device__ inline void gf_ws_plan(int y0, int y1, GfWsPlan<NS>& pl)
+__host__ __device__ inline void gf_ws_plan(int y0, int y1, int pen, GfWsPlan<NS>& pl)
 {
     const int H = y1 - y0;
-    // balance: an outer boundary costs its stream ~R more full rows, so the first and the last stream get
-    // `pen` rows fewer; every stream of a shared plan needs at least R+1 rows
-    const int pen = (R * 7) / 8;
+    // balance: an outer boundary costs its stream R more producer rows, a shared END costs its consumer R more steps after
+    // the producers have finished (measured with -DGF_WS_TIMING: ~0.6 producer rows each), so the first and the last stream
+    // get `pen` ~ 3R/8 rows fewer than the inner ones; every stream of a shared plan needs at least R+1 rows
     int Ls[NS];
     int n = NS;
     for (; n > 1; --n) {
@@ -809,7 +811,7 @@ __global__ void __launch_bounds__((SPLIT ? 96 : 64) * NS, 1) gf_ws_gray_kernel(c
         gf_ws_bar_init(reinterpret_cast<unsigned long long*>(const_cast<int*>(ctrl) + 16) + i);
     __syncthreads();
     GfWsPlan<NS> pl;
-    gf_ws_plan<R, NS>(y0, y1, pl);
+    gf_ws_plan<R, NS>(y0, y1, a.pen, pl);
     // strips tile the width in steps of WOUT; the LAST one is pulled back so that its window ends exactly HALO columns
     // past the image (its mirror is then the compile-time twin of the first strip's) and writes only the columns
     // the strip before it left over
@@ -819,6 +821,14 @@ __global__ void __launch_bounds__((SPLIT ? 96 : 64) * NS, 1) gf_ws_gray_kernel(c
     if (strip == a.nstrips - 1 && a.nstrips > 1 && a.width + G::HALO - G::WIN >= 0) xl = a.width + G::HALO - G::WIN;
     const int k = warp % NS, part = warp / NS;
     if (k >= pl.n) return;
+#ifdef GF_WS_TIMING
+    const long long t_start = clock64();
+    struct DbgStamp {
+        long long* p; long long t0; int lane; int info0, info1;
+        __device__ ~DbgStamp() { if (p && lane == 0) { p[0] = t0; p[1] = clock64(); p[2] = info0; p[3] = info1; } }
+    } dbg_stamp{a.dbg ? a.dbg + ((long long)blockIdx.x * (3 * NS) + warp) * 4 : nullptr, t_start, lane,
+                (strip << 16) | band, (pl.s[k].L << 16) | ((pl.s[k].m1 - pl.s[k].m0) & 0xffff)};
+#endif
     const bool in_l = xl >= 0, in_r = xl + G::WIN <= a.width;
     const int em = (in_l && in_r) ? 0 : ((xl == -G::HALO && in_r) ? 1 : ((in_l && xl + G::WIN == a.width + G::HALO) ? 2 : 3));
 #define GF_WS_S1(ROLE)                                                                                                   \
@@ -908,6 +918,12 @@ static const char* gf_ws_launch(const Job& j)
     a.width = j.width; a.height = j.height; a.buf_y0 = j.buf_y0; a.buf_rows = j.buf_rows; a.out_y0 = j.out_y0;
     a.out_rows = j.out_rows; a.border = j.border; a.eps = j.eps; a.count = j.count;
     a.nstrips = (j.width + G::WOUT - 1) / G::WOUT;
+    a.pen = GF_KNOB("GF_WS_PEN", (3 * R) / 8);
+    if (a.pen > 2 * R) a.pen = 2 * R;
+    a.dbg = nullptr;
+#ifdef GF_WS_TIMING
+    a.dbg = (long long*)(((unsigned long long)(unsigned)GF_KNOB("GF_WS_DBG_HI", 0) << 31) | (unsigned long long)(unsigned)GF_KNOB("GF_WS_DBG_LO", 0));
+#endif
     GfWsBands bd = gf_ws_pick_bands<R, NS>(j.out_rows, a.nstrips, j.count, sms, GF_KNOB("GF_WS_EDGE_PCT", 135));
     if (GF_KNOB_SET("GF_WS_HB")) {
         int hb = GF_KNOB("GF_WS_HB", bd.hb);
@@ -944,10 +960,15 @@ static const char* gf_ws_launch(const Job& j)
 static const char* gf_ws_try(const Job& j, bool* done, const char** name)
 {
     *done = false;
-    // default: jobs that want the a / b planes (hGuidedFilter's d_A, d_B through the drop-in shim) -- the producer warps store
+    // default ON for: jobs that want the a / b planes (hGuidedFilter's d_A, d_B through the drop-in shim) -- the producer warps store
     // them on the side, where the round-1 kernels fall back to their first generation (wp: 103 us at 4K r=8); plain jobs
     // stay on gf_s8, which is as fast at 4K and faster above
-    if (j.color || !GF_KNOB("GF_WS", j.A.ptr ? 1 : GF_WS_DEFAULT) || GF_KNOB("GF_DISABLE_FAST", 0)) return nullptr;
+    // ... and single frames of up to 12 Mpx at r = 8 (the headline shape: 62.4 us against 65.7 us at 4K, 35.5 against 37.1 at
+    // 1080p; above that size gf_s8's steady state wins: 8K 192 vs 170 us, profiles/r2_ws_matrix_final.jsonl, r2_ws_pen.jsonl)
+    const bool small_r8 = j.r == 8 && j.count == 1 && (int64_t)j.width * j.out_rows <= 12000000;
+    if (j.color || !GF_KNOB("GF_WS", (j.A.ptr || small_r8) ? 1 : GF_WS_DEFAULT) || GF_KNOB("GF_DISABLE_FAST", 0) ||
+        GF_KNOB("GF_DISABLE_S8", 0))          // (GF_DISABLE_S8 = "first-generation kernels only" in the differential tests)
+        return nullptr;
     const int force_k = GF_KNOB("GF_WS_K", 0);
     if ((j.A.ptr == nullptr) != (j.B.ptr == nullptr)) return nullptr;
     const Plane* pl[5] = {&j.guide, &j.src, &j.dst, &j.A, &j.B};

@@ -48,10 +48,11 @@ S8_RADII = (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32)
 
 @pytest.mark.parametrize("border", [0, 1, 2])
 @pytest.mark.parametrize("r", S8_RADII)
-def test_gray_s8_every_radius(be, r, border):
+def test_gray_s8_every_radius(be, r, border, knob):
     """The headline kernel family (gf_s8.cuh) at every radius it is instantiated for: interior
     strips, border strips (analytic edges at r=8, mirror loads for REFLECT101, the generic column
     map for REFLECT, clipped-window counts for TRUNCATE), several bands, a width that is / is not a multiple of 8."""
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     for (h, w) in ((300, 960), (270, 1004)):
         I, p = synth_pair(h, w, seed=100 + r, kind="structured")
         q = be.guided_gray(I, p, r, 1e-2, border, pad=(-w) % 8)
@@ -61,9 +62,10 @@ def test_gray_s8_every_radius(be, r, border):
         assert np.abs(q - ref).max() <= TOL
 
 
-def test_gray_8k_r8_and_giga_strip_r16(be):
+def test_gray_8k_r8_and_giga_strip_r16(be, knob):
     """Larger-than-4K frames take the multi-wave path of the s8 kernel (bands of hb_max rows);
     a 4096-row strip of a 32768-wide image is the per-GPU unit of BASELINE config 5 (r=16)."""
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     I, p = synth_pair(4320, 7680, seed=4)
     q = be.guided_gray(I, p, 8, 1e-2, 0)
     assert be.api.last_kernel() == "s8_r8"
@@ -232,6 +234,7 @@ def test_no_out_of_bounds_access(be):
 def test_long_bands_do_not_drift(be, knob):
     """Large batches / tall strips make the band chooser pick full-height bands: the running sums
     then run for the whole image (colour: no re-seed; gray: re-seeded every 2r+1 rows)."""
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     I3 = np.random.default_rng(100).random((1080, 1920, 3), dtype=np.float32)
     p = np.random.default_rng(10000).random((1080, 1920), dtype=np.float32)
     knob(be, "GF_C4_HB", 1080)
@@ -304,9 +307,10 @@ def test_class_run_channel_pairs(be):
     assert np.abs(q - O.guided_filter_color(g3, g1, 5, 0.05, O.BORDER_TRUNCATE)).max() <= TOL
 
 
-def test_class_run_planar_1080p(be):
+def test_class_run_planar_1080p(be, knob):
     """The reference's own path-A demo shape (main.cpp:109-150): 1080p, gray guide, 3-channel source,
     r=7, eps=0.3 -- and the (3,3) mode -- take the planar s8 path."""
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     rng = np.random.default_rng(21)
     g1 = rng.random((1080, 1920), dtype=np.float32)
     g3 = rng.random((1080, 1920, 3), dtype=np.float32)

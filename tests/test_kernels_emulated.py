@@ -194,6 +194,7 @@ def test_gray_s8(be, shape, r, border, knob):
     several bands (GF_S8_HB), a width that is not a multiple of 8 (partial last lane), heights that
     end inside / right after a re-seed period; the last case has warps that are interior in a
     TRUNCATE job (plain code) next to clipped ones."""
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     knob(be, "GF_S8_HB", 2 * r + 9)
     I, p = synth_pair(*shape, seed=71, kind="structured")
     w = shape[1]
@@ -205,6 +206,7 @@ def test_gray_s8(be, shape, r, border, knob):
 @pytest.mark.parametrize("shape,r,border", [((90, 1000), 8, 0), ((100, 960), 4, 0), ((120, 1000), 8, 1)])
 def test_gray_s8_two_band_classes(be, shape, r, border, knob):
     """the first and last strip in shorter bands than the interior strips (GF_S8_EDGE_PCT): item -> (strip, band) mapping"""
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     knob(be, "GF_S8_HB", 40)
     knob(be, "GF_S8_EDGE_PCT", 65)
     I, p = synth_pair(*shape, seed=73, kind="structured")
@@ -220,6 +222,7 @@ def test_gray_s8_tape(be, shape, r, border, slots, pct, knob):
     """tape scheduling (gf_tape_run): pieces shorter than a strip, pieces that cross strips, pieces that
     span several strips (few slots), weighted edge strips, one piece for the whole job.  (The uniform
     split differs in the last bits only: the running sums are re-seeded relative to the band start.)"""
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     knob(be, "GF_TAPE", 1)
     knob(be, "GF_TAPE_SLOTS", slots)
     knob(be, "GF_S8_EDGE_PCT", pct)
@@ -234,6 +237,7 @@ def test_gray_s8_tape(be, shape, r, border, slots, pct, knob):
 
 def test_tape_batch(be, knob):
     """pieces that cross from one frame into the next (gray and colour batches)"""
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     rng = np.random.default_rng(18)
     knob(be, "GF_TAPE", 1)
     knob(be, "GF_TAPE_SLOTS", 5)
@@ -254,7 +258,8 @@ def test_tape_batch(be, knob):
             assert np.abs(q[k] - O.guided_filter_color(I[k], p[k], 8, 1e-2, 0)).max() <= TOL
 
 
-def test_gray_s8_batch_strip_kat(be):
+def test_gray_s8_batch_strip_kat(be, knob):
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     rng = np.random.default_rng(8)
     Ib = rng.random((2, 40, 320), dtype=np.float32)
     pb = rng.random((2, 40, 320), dtype=np.float32)
@@ -303,9 +308,10 @@ def test_color_c4_batch(be):
         assert np.abs(q[k] - O.guided_filter_color(I[k], p[k], 8, 1e-2, 0)).max() <= TOL
 
 
-def test_class_run_planar_path(be):
+def test_class_run_planar_path(be, knob):
     """The class API's (1,3) and (3,3) modes on the tuned kernel: channels de-interleaved into scratch
     planes, one s8 launch over the channels, re-interleaved (TRUNCATE border, as GuidedFilter::run)."""
+    knob(be, "GF_WS", 0)          # this test is about the s8 kernel; gf_ws is the default for 4K-class r = 8 frames
     rng = np.random.default_rng(16)
     g1 = rng.random((40, 264), dtype=np.float32)
     g3 = rng.random((40, 264, 3), dtype=np.float32)
