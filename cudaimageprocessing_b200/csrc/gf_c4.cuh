@@ -15,9 +15,10 @@
 //     shared memory (one float4 per lane, quantity and row: conflict-free LDS.128/STS.128);
 //   * q = mean_a . I + mean_b; the guide row of the output is the row that leaves the stage-1
 //     window in the same iteration (re-read from L2, never parked);
-//   * image borders (REFLECT101, width % 4 == 0): lanes outside the image take their rows from
-//     the mirror lanes by shuffle (32 extra SHFL per iteration, border strips only); any other
-//     border/width uses the generic kernel.
+//   * image borders (width % 4 == 0), template BM: 0 REFLECT101 and 1 REFLECT -- lanes outside the image take
+//     their rows from the mirror lanes by shuffle (32 extra SHFL per iteration, border strips only); 2 TRUNCATE
+//     (the class API's border, guided_filter.cpp:22-60) -- rows and lanes outside the image are zeros and every
+//     mean divides by its own in-image pixel count; any other width uses the generic kernel.
 // R must be a multiple of 4 and <= 16 (M <= 4 halo lanes per side and stage).
 #pragma once
 #include "gf_s8.cuh"
@@ -70,6 +71,8 @@ struct GfC4Ctx {
     bool ring_lane, out_lane, mirror, out_l, out_r, src_l;   // mirror: this warp overhangs the image
     int s0, s1, s2;                                  // mirror source lanes for column j = 0, j = 1..2, j = 3
     float eps;
+    float icx[4];                                    // BM 2: 1 / (in-image columns of the window of column j)
+    bool nz, oz;                                     // BM 2: nI/nP (oI/oP) stand for a row outside the image: zeros
     float c[13][4];                                  // stage-1 column sums
     float sa[4][4];                                  // stage-2 running sums (a_r, a_g, a_b, b)
     float va[4][4];                                  // a, b of the row produced by the previous iteration
@@ -89,33 +92,48 @@ __device__ __forceinline__ void gf_c4_ld(const GfC4Ctx<R>& c, int row_ofs_I, int
     vp[0] = tp.x; vp[1] = tp.y; vp[2] = tp.z; vp[3] = tp.w;
 }
 
-// REFLECT101 mirror for lanes outside the image (width % 4 == 0):
+// Mirror for lanes outside the image (width % 4 == 0).  REFLECT101:
 //   left : column -4k+j <- column 4k-j      = {col0 of lane s0, col3, col2, col1 of lane s1}
 //   right: column W+4m+j <- column W-2-4m-j = {col2, col1, col0 of lane s1(=s0), col3 of lane s2}
-// A warp overhangs at most one side (width >= 128), so all its lanes publish that side's pattern.
-template <int R>
-__device__ __forceinline__ void gf_c4_mirror(const GfC4Ctx<R>& c, float (&vi)[12], float (&vp)[4])
+// REFLECT (edge pixel repeated): column -4k+j <- 4k-1-j and W+4m+j <- W-1-4m-j: the four columns of ONE lane (s0), reversed.
+// TRUNCATE: zeros.  A warp overhangs at most one side (width >= 128), so all its lanes publish that side's pattern.
+template <int R, int BM>
+__device__ __forceinline__ void gf_c4_mirror(const GfC4Ctx<R>& c, float (&vi)[12], float (&vp)[4], bool zero_row = false)
 {
     const unsigned full = 0xffffffffu;
     const bool out = c.out_l || c.out_r;
+    if (BM == 2) {                                  // (also run by interior strips: rows above / below the image)
+        const bool z = out || zero_row;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) vi[i] = z ? 0.f : vi[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vp[j] = z ? 0.f : vp[j];
+        return;
+    }
     // per destination column j: source column index in the source lane (left pattern / right pattern)
-    //   j:      0  1  2  3
-    //   left:   0  3  2  1      lanes: s0 s1 s1 s1
-    //   right:  2  1  0  3      lanes: s0 s0 s0 s2   (s1 == s0 for right lanes)
+    //   REFLECT101  j:  0  1  2  3          REFLECT  j:  0  1  2  3
+    //   left:           0  3  2  1   s0 s1 s1 s1         3  2  1  0   s0 s0 s0 s0
+    //   right:          2  1  0  3   s0 s0 s0 s2         3  2  1  0   s0 s0 s0 s0     (s1 == s0 for right lanes)
     float ni[12], np[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int jl = j == 0 ? 0 : 4 - j, jr = j == 3 ? 3 : 2 - j;
-        const int sl = j == 0 ? c.s0 : c.s1;
-        const int sr = j == 3 ? c.s2 : c.s0;
-        const int srcl = c.out_l ? sl : sr;
+        if (BM == 1) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float pub = c.src_l ? vi[3 * jl + ch] : vi[3 * jr + ch];
-            ni[3 * j + ch] = __shfl_sync(full, pub, srcl);
+            for (int ch = 0; ch < 3; ++ch) ni[3 * j + ch] = __shfl_sync(full, vi[3 * (3 - j) + ch], c.s0);
+            np[j] = __shfl_sync(full, vp[3 - j], c.s0);
+        } else {
+            const int jl = j == 0 ? 0 : 4 - j, jr = j == 3 ? 3 : 2 - j;
+            const int sl = j == 0 ? c.s0 : c.s1;
+            const int sr = j == 3 ? c.s2 : c.s0;
+            const int srcl = c.out_l ? sl : sr;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float pub = c.src_l ? vi[3 * jl + ch] : vi[3 * jr + ch];
+                ni[3 * j + ch] = __shfl_sync(full, pub, srcl);
+            }
+            const float pubp = c.src_l ? vp[jl] : vp[jr];
+            np[j] = __shfl_sync(full, pubp, srcl);
         }
-        const float pubp = c.src_l ? vp[jl] : vp[jr];
-        np[j] = __shfl_sync(full, pubp, srcl);
     }
 #pragma unroll
     for (int i = 0; i < 12; ++i) vi[i] = out ? ni[i] : vi[i];
@@ -123,14 +141,18 @@ __device__ __forceinline__ void gf_c4_mirror(const GfC4Ctx<R>& c, float (&vi)[12
     for (int j = 0; j < 4; ++j) vp[j] = out ? np[j] : vp[j];
 }
 
-template <int R, bool MIRROR>
-__device__ __forceinline__ void gf_c4_load_row(const GfC4Ctx<R>& c, int y, float (&vi)[12], float (&vp)[4])
+// Returns true when the row stands for zeros (TRUNCATE, row outside the image or past the resident rows): the loads are
+// issued anyway, from a clamped row, so that the load schedule has no branch; gf_c4_mirror<.., 2> clears the values.
+template <int R, bool MIRROR, int BM>
+__device__ __forceinline__ bool gf_c4_load_row(const GfC4Ctx<R>& c, int y, float (&vi)[12], float (&vp)[4])
 {
-    int rn = gf_s8_map_y(y, c.height, c.border);
+    int rn = BM == 2 ? (y < 0 ? 0 : y) : gf_s8_map_y(y, c.height, c.border);
+    const bool zero = BM == 2 && (y < 0 || y > c.buf_ylast);
     rn = rn > c.buf_ylast ? c.buf_ylast : rn;
     const int o = rn - c.buf_y0;
     gf_c4_ld<R>(c, o * c.gs, o * c.ss, vi, vp);     // RAW for lanes outside the image: gf_c4_mirror runs where the row is
                                                     // consumed (shuffles right behind the loads would wait for them here)
+    return zero;
 }
 
 // the 13 products of one pixel, added to (SUB = false) or removed from (SUB = true) the column sums
@@ -146,14 +168,14 @@ __device__ __forceinline__ void gf_c4_accum(float (&c)[13][4], int j, float i0, 
 }
 
 // Iteration t >= 2R (see gf_s8_iter for the schedule: ramp-up is data, not code).
-template <int R, bool MIRROR>
+template <int R, bool MIRROR, int BM>
 __device__ __forceinline__ void gf_c4_iter(GfC4Ctx<R>& c, int t, int slot, bool full)
 {
     using G = GfC4Geom<R>;
     constexpr int KW = G::KW, VL = G::VL;
     const int yi = c.yi0 + t;
 
-    if (MIRROR) { gf_c4_mirror<R>(c, c.nI, c.nP); gf_c4_mirror<R>(c, c.oI, c.oP); }
+    if (MIRROR || BM == 2) { gf_c4_mirror<R, BM>(c, c.nI, c.nP, c.nz); gf_c4_mirror<R, BM>(c, c.oI, c.oP, c.oz); }
     // ---- stage 1, vertical: add row yi, drop row yi - KW (its guide pixels are kept for the output)
     float gI[12];
 #pragma unroll
@@ -164,8 +186,8 @@ __device__ __forceinline__ void gf_c4_iter(GfC4Ctx<R>& c, int t, int slot, bool 
         gf_c4_accum<true>(c.c, j, c.oI[3 * j], c.oI[3 * j + 1], c.oI[3 * j + 2], c.oP[j]);
     }
     // rows of the next iteration
-    gf_c4_load_row<R, MIRROR>(c, yi + 1, c.nI, c.nP);
-    gf_c4_load_row<R, MIRROR>(c, yi + 1 - KW, c.oI, c.oP);
+    c.nz = gf_c4_load_row<R, MIRROR, BM>(c, yi + 1, c.nI, c.nP);
+    c.oz = gf_c4_load_row<R, MIRROR, BM>(c, yi + 1 - KW, c.oI, c.oP);
 
     // ---- stage 2 of the a, b row produced by the previous iteration
     {
@@ -189,11 +211,12 @@ __device__ __forceinline__ void gf_c4_iter(GfC4Ctx<R>& c, int t, int slot, bool 
         if (full) {                                   // q of row yo = yi-1-2R; guide row gI
             const int yo = yi - 1 - 2 * R;
             const float inv = 1.0f / (float)(KW * KW);
+            const float icy = BM == 2 ? 1.0f / gf_s8_cnt_y<R>(yo, c.height) : 0.f;
             float qv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float v = fmaf(c.sa[0][j], gI[3 * j], fmaf(c.sa[1][j], gI[3 * j + 1], fmaf(c.sa[2][j], gI[3 * j + 2], c.sa[3][j])));
-                qv[j] = v * inv;
+                qv[j] = v * (BM == 2 ? c.icx[j] * icy : inv);
             }
             if (c.out_lane) *reinterpret_cast<float4*>(c.gQ + (yo - c.out_y0) * c.ds) = make_float4(qv[0], qv[1], qv[2], qv[3]);
         }
@@ -204,9 +227,13 @@ __device__ __forceinline__ void gf_c4_iter(GfC4Ctx<R>& c, int t, int slot, bool 
         float h[13][4];
 #pragma unroll
         for (int q = 0; q < 13; ++q) gf_c4_window<R>(c.c[q], h[q]);
-        const float inv = 1.0f / (float)(KW * KW);
+        const float inv1 = 1.0f / (float)(KW * KW);
+        const int yc = yi - R;
+        const float icy = BM == 2 ? 1.0f / gf_s8_cnt_y<R>(yc, c.height) : 0.f;
+        const bool ok = BM != 2 || (!(c.out_l || c.out_r) && yc >= 0 && yc < c.height);     // TRUNCATE: a, b are zero outside the image
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            const float inv = BM == 2 ? c.icx[j] * icy : inv1;
             const float m0 = h[0][j] * inv, m1 = h[1][j] * inv, m2 = h[2][j] * inv, mp = h[3][j] * inv;
             const float c0 = fmaf(h[4][j], inv, -m0 * mp), c1 = fmaf(h[5][j], inv, -m1 * mp), c2 = fmaf(h[6][j], inv, -m2 * mp);
             const float s00 = fmaf(h[7][j], inv, -m0 * m0) + c.eps, s01 = fmaf(h[8][j], inv, -m0 * m1),
@@ -220,13 +247,13 @@ __device__ __forceinline__ void gf_c4_iter(GfC4Ctx<R>& c, int t, int slot, bool 
             const float a0 = (i00 * c0 + i01 * c1 + i02 * c2) * rd;
             const float a1 = (i01 * c0 + i11 * c1 + i12 * c2) * rd;
             const float a2 = (i02 * c0 + i12 * c1 + i22 * c2) * rd;
-            c.va[0][j] = a0; c.va[1][j] = a1; c.va[2][j] = a2;
-            c.va[3][j] = mp - (a0 * m0 + a1 * m1 + a2 * m2);
+            c.va[0][j] = ok ? a0 : 0.f; c.va[1][j] = ok ? a1 : 0.f; c.va[2][j] = ok ? a2 : 0.f;
+            c.va[3][j] = ok ? mp - (a0 * m0 + a1 * m1 + a2 * m2) : 0.f;
         }
     }
 }
 
-template <int R, bool MIRROR>
+template <int R, bool MIRROR, int BM>
 __device__ __forceinline__ void gf_c4_band(GfC4Ctx<R>& c, int steps)
 {
     constexpr int KW = 2 * R + 1;
@@ -234,13 +261,15 @@ __device__ __forceinline__ void gf_c4_band(GfC4Ctx<R>& c, int steps)
     // the band start costs 2R/4 DRAM latencies instead of 2R (2R is a multiple of 4: R % 4 == 0)
     {
         float bI[4][12], bP[4][4];
+        bool bz[4];
 #pragma unroll 1
         for (int t = 0; t < 2 * R; t += 4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) gf_c4_load_row<R, MIRROR>(c, c.yi0 + t + 1 + k, bI[k], bP[k]);
+            for (int k = 0; k < 4; ++k) bz[k] = gf_c4_load_row<R, MIRROR, BM>(c, c.yi0 + t + 1 + k, bI[k], bP[k]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (MIRROR) gf_c4_mirror<R>(c, c.nI, c.nP);
+                if (MIRROR || BM == 2) gf_c4_mirror<R, BM>(c, c.nI, c.nP, c.nz);
+                c.nz = bz[k];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) gf_c4_accum<false>(c.c, j, c.nI[3 * j], c.nI[3 * j + 1], c.nI[3 * j + 2], c.nP[j]);
 #pragma unroll
@@ -256,12 +285,12 @@ __device__ __forceinline__ void gf_c4_band(GfC4Ctx<R>& c, int steps)
     while (t <= steps) {
         const int n = steps + 1 - t < KW ? steps + 1 - t : KW;
 #pragma unroll 1
-        for (int s = 0; s < n; ++s, ++t) gf_c4_iter<R, MIRROR>(c, t, s, full);
+        for (int s = 0; s < n; ++s, ++t) gf_c4_iter<R, MIRROR, BM>(c, t, s, full);
         full = true;
     }
 }
 
-template <int R, int MINB>
+template <int R, int MINB, int BM>
 __global__ void __launch_bounds__(32, MINB) gf_c4_color_kernel(const GF_GRID_CONSTANT GfWpArgs a)
 {
     using G = GfC4Geom<R>;
@@ -280,7 +309,7 @@ __global__ void __launch_bounds__(32, MINB) gf_c4_color_kernel(const GF_GRID_CON
         const int lw = (a.width - xl) / 4 - 1;       // last lane inside the image (may be >= 32: then no lane is out_r)
         const int X = 4 * M - c.lane;                // left: lane of column -x0 (j = 0)
         const int Y = 2 * lw + 1 - c.lane;           // right: lane of column W-2-(x0-W) (j = 0..2)
-        c.s0 = c.out_l ? X : Y;
+        c.s0 = c.out_l ? (BM == 1 ? X - 1 : X) : Y;  // REFLECT: the whole lane comes from lane X-1 (left) or Y (right)
         c.s1 = c.out_l ? X - 1 : Y;
         c.s2 = Y - 1;
         // lanes far outside the image (beyond the 2M halo lanes) mirror nothing anyone uses: clamp
@@ -306,6 +335,9 @@ __global__ void __launch_bounds__(32, MINB) gf_c4_color_kernel(const GF_GRID_CON
     c.yi0 = yo0 - 2 * R;
     c.eps = a.eps;
 #pragma unroll
+    for (int j = 0; j < 4; ++j) c.icx[j] = BM == 2 ? 1.0f / gf_count(c.x0 + j, a.width, R, GF_TRUNCATE) : 0.f;
+    c.oz = true;
+#pragma unroll
     for (int q = 0; q < 13; ++q)
 #pragma unroll
         for (int j = 0; j < 4; ++j) c.c[q][j] = 0.f;
@@ -320,11 +352,11 @@ __global__ void __launch_bounds__(32, MINB) gf_c4_color_kernel(const GF_GRID_CON
     (void)VL;
     const int steps = (yo1 - yo0) + 4 * R;
     if (c.mirror) {
-        gf_c4_load_row<R, true>(c, c.yi0, c.nI, c.nP);
-        gf_c4_band<R, true>(c, steps);
+        c.nz = gf_c4_load_row<R, true, BM>(c, c.yi0, c.nI, c.nP);
+        gf_c4_band<R, true, BM>(c, steps);
     } else {
-        gf_c4_load_row<R, false>(c, c.yi0, c.nI, c.nP);
-        gf_c4_band<R, false>(c, steps);
+        c.nz = gf_c4_load_row<R, false, BM>(c, c.yi0, c.nI, c.nP);
+        gf_c4_band<R, false, BM>(c, steps);
     }
     };
     gf_tape_run(a, (long long)blockIdx.x, run);
@@ -372,16 +404,21 @@ static const char* gf_c4_launch(const Job& j)
     if (!GF_KNOB_SET("GF_C4_HB"))
         if (const long n = gf_tape_plan(a, R, (long)sms * warps_sm, 2 * R + 8, we, tape_dflt)) items = n;
     dim3 grid((unsigned)items), block(32);
-    auto k = gf_c4_color_kernel<R, MINB>;
-    if (const char* e = gf_rt_set_smem(k, smem)) return e;
-    GF_LAUNCH(k, grid, block, smem, j.stream, a);
-    return gf_rt_launch_error();
+    auto go = [&](auto k) -> const char* {
+        if (const char* e = gf_rt_set_smem(k, smem)) return e;
+        GF_LAUNCH(k, grid, block, smem, j.stream, a);
+        return gf_rt_launch_error();
+    };
+    if (j.border == GF_REFLECT) return go(gf_c4_color_kernel<R, MINB, 1>);
+    if (j.border == GF_TRUNCATE) return go(gf_c4_color_kernel<R, MINB, 2>);
+    return go(gf_c4_color_kernel<R, MINB, 0>);
 }
 
 static const char* gf_c4_try(const Job& j, bool* done, const char** name)
 {
     *done = false;
-    if (!j.color || j.border != GF_REFLECT101 || j.A.ptr) return nullptr;
+    if (!j.color || j.A.ptr) return nullptr;
+    if (j.border != GF_REFLECT101 && j.border != GF_REFLECT && j.border != GF_TRUNCATE) return nullptr;
     if (GF_KNOB("GF_DISABLE_C4", 0) || GF_KNOB("GF_DISABLE_FAST", 0)) return nullptr;
     if (j.guide.channels != 3 || j.guide.coff != 0 || j.src.channels != 1 || j.src.coff != 0 || j.dst.channels != 1 || j.dst.coff != 0)
         return nullptr;

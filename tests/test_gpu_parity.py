@@ -119,13 +119,13 @@ def test_kat_crops_u8(be, crop):
     assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 2
 
 
-@pytest.mark.parametrize("border", [0, 1])
+@pytest.mark.parametrize("border", [0, 1, 2])
 def test_color_1080p_r16(be, border):
     """BASELINE config 3 frame: 1920x1080 RGB guide, 1-channel src, r=16, eps=1e-2."""
     I3 = np.random.default_rng(100).random((1080, 1920, 3), dtype=np.float32)
     p = np.random.default_rng(10000).random((1080, 1920), dtype=np.float32)
     q = be.guided_color(I3, p, 16, 1e-2, border)
-    assert be.api.last_kernel() == ("c4_r16" if border == 0 else "generic_color")
+    assert be.api.last_kernel() == "c4_r16"       # all three border rules run the tuned kernel (TRUNCATE = the class API's)
     ref = O.guided_filter_color(I3, p, 16, 1e-2, border, np.float64)      # float64 oracle (north_star); parity unpinned (no reference golden)
     err = np.abs(q - ref).max()
     print(f"colour 1080p r=16 border={border}: max err {err:.3e}")
@@ -173,10 +173,11 @@ def test_fuzz_c4_against_generic_kernel(be, knob):
         h = int(rng.integers(4 * r + 2, 4 * r + 200))
         w = 4 * int(rng.integers(32, 400))
         n = int(rng.integers(1, 4))
+        border = int(rng.integers(0, 3))
         I = torch.rand((n, h, w, 3), device="cuda", generator=g)
         p = torch.rand((n, h, w), device="cuda", generator=g)
         q1, q0 = torch.empty_like(p), torch.empty_like(p)
-        args = (n, w, h, 3, 0, 0, 0, 0, 0, 0, r, 1e-2, 0, None)
+        args = (n, w, h, 3, 0, 0, 0, 0, 0, 0, r, 1e-2, border, None)
         be.api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q1.data_ptr(), *args)
         assert be.api.last_kernel() == f"c4_r{r}"
         knob(be, "GF_DISABLE_FAST", 1)
@@ -185,7 +186,7 @@ def test_fuzz_c4_against_generic_kernel(be, knob):
         torch.cuda.synchronize()
         assert be.api.last_kernel() == "generic_color"
         d = float((q1 - q0).abs().max())
-        assert d <= 5e-5, (it, n, h, w, r, d)
+        assert d <= 5e-5, (it, n, h, w, r, border, d)
         worst = max(worst, d)
     print(f"fuzz colour: worst |tuned - generic| = {worst:.2e}")
 
@@ -305,6 +306,17 @@ def test_class_run_channel_pairs(be):
         assert np.abs(q - O.guided_filter_class_run(I, p, 7, 0.3)).max() <= TOL
     q = be.class_run(g3, g1, 5, 0.05)
     assert np.abs(q - O.guided_filter_color(g3, g1, 5, 0.05, O.BORDER_TRUNCATE)).max() <= TOL
+
+
+def test_class_run_color_guide_tuned(be):
+    """GuidedFilter::run with a 3-channel guide and a 1-channel source (TRUNCATE border) runs the tuned colour kernel."""
+    rng = np.random.default_rng(61)
+    g3 = rng.random((540, 960, 3), dtype=np.float32)
+    p = rng.random((540, 960), dtype=np.float32)
+    q = be.class_run(g3, p, 8, 1e-2)
+    assert be.api.last_kernel() == "c4_r8"
+    ref = O.guided_filter_color(g3, p, 8, 1e-2, O.BORDER_TRUNCATE, np.float64)
+    assert np.abs(q - ref).max() <= TOL
 
 
 def test_class_run_planar_1080p(be, knob):

@@ -285,17 +285,29 @@ def test_gray_s8_batch_strip_kat(be, knob):
 
 
 # ---- the tuned colour-guide kernel (gf_c4.cuh) under the emulator --------------------------------
+@pytest.mark.parametrize("border", [0, 1, 2])
 @pytest.mark.parametrize("shape,r", [((40, 160), 4), ((50, 256), 8), ((60, 132), 12), ((80, 192), 16)])
-def test_color_c4(be, shape, r, knob):
-    """interior strips, border strips (mirror shuffles on both image edges), several bands."""
+def test_color_c4(be, shape, r, border, knob):
+    """interior strips, border strips (mirror shuffles / zero fill on both image edges), several bands; all three
+    border rules (REFLECT101, the class API's TRUNCATE, REFLECT)."""
     knob(be, "GF_C4_HB", 2 * r + 9)
     h, w = shape
     rng = np.random.default_rng(40 + r)
     I3 = rng.random((h, w, 3), dtype=np.float32)
     p = rng.random((h, w), dtype=np.float32)
-    q = be.guided_color(I3, p, r, 1e-2, 0)
+    q = be.guided_color(I3, p, r, 1e-2, border)
     assert be.api.last_kernel() == f"c4_r{r}"
-    assert np.abs(q - O.guided_filter_color(I3, p, r, 1e-2, 0)).max() <= TOL
+    assert np.abs(q - O.guided_filter_color(I3, p, r, 1e-2, border)).max() <= TOL
+
+
+def test_class_run_color_guide_c4(be):
+    """the class API (TRUNCATE) with a colour guide and a 1-channel source takes the tuned kernel"""
+    rng = np.random.default_rng(62)
+    g3 = rng.random((44, 136, 3), dtype=np.float32)
+    p = rng.random((44, 136), dtype=np.float32)
+    q = be.class_run(g3, p, 8, 1e-2)
+    assert be.api.last_kernel() == "c4_r8"
+    assert np.abs(q - O.guided_filter_color(g3, p, 8, 1e-2, O.BORDER_TRUNCATE)).max() <= TOL
 
 
 def test_color_c4_batch(be):
