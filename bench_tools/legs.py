@@ -139,8 +139,9 @@ def config5(torch, dist, api, pkg, rank, world, barrier, size=32768, steps=3, r=
            "n_gpus": world, "rows_per_gpu": y1 - y0, "ms_total": ms_all, "ms_kernel": ms_k, "ms_halo_exchange": max(0.0, ms_all - ms_k),
            "mpix_s": px / ms_all / 1e3, "alg_gb_s_per_gpu": 12.0 * px / world / ms_k / 1e6,
            "halo_bytes_per_neighbour": 2 * r * W * 4 * 2, "kernel": kern,
-           "exchange": "gf_run_strips: peer copies of the 2r halo rows out of the neighbours' IPC-mapped strip buffers (copy engines over NVLink), "
-                       "then the strip kernel on the same stream; ranks are barrier-synchronised around the step",
+           "exchange": "gf_run_strips: one kernel pulls the 2r halo rows out of the neighbours' IPC-mapped strip buffers over NVLink, the "
+                       "strip kernel follows on the same stream; ranks are barrier-synchronised around the step. ms_halo_exchange = ms_total "
+                       "- the strip kernel alone (pull + launch gap after an idle GPU; at 1 GPU, with no pull at all, it is the launch gap)",
            "seam_check": {"max_abs_err_vs_oracle_f64": err, "rows_per_rank": checked, "what": f"first and last {seam_rows} output rows of every "
                           "rank's strip (both sides of every seam) against oracle/gf_oracle.c in float64 on regenerated rows", "seconds": t_check},
            "steps": steps}

@@ -654,18 +654,26 @@ int gf_guided_batch(const float* guide, const float* src, float* dst, int count,
     return run_jobs(&j, 1);
 }
 
-int gf_guided_gray_strip(const float* guide, const float* src, float* dst, int width, int global_height, int buf_y0,
-                         int buf_rows, int out_y0, int out_rows, int64_t guide_stride, int64_t src_stride,
-                         int64_t dst_stride, int r, float eps, int border, void* stream)
+static Job strip_job(const float* guide, const float* src, float* dst, int width, int global_height, int buf_y0, int buf_rows, int out_y0,
+                     int out_rows, int64_t guide_stride, int64_t src_stride, int64_t dst_stride, int r, float eps, int border, void* stream)
 {
     Job j;
     j.width = width; j.height = global_height; j.buf_y0 = buf_y0; j.buf_rows = buf_rows; j.out_y0 = out_y0; j.out_rows = out_rows;
     j.r = r; j.eps = eps; j.border = border; j.stream = stream;
-    if (buf_rows <= 0 || buf_y0 < 0 || buf_y0 + buf_rows > global_height) return fail(GF_ERR_INVALID, "buffer rows outside the image");
     j.guide = Plane{guide, or_packed(guide_stride, width, 1), 0, 1, 0};
     j.src = Plane{src, or_packed(src_stride, width, 1), 0, 1, 0};
     j.dst = Plane{dst, or_packed(dst_stride, width, 1), 0, 1, 0};
     j.A = j.B = Plane{nullptr, 0, 0, 1, 0};
+    return j;
+}
+
+int gf_guided_gray_strip(const float* guide, const float* src, float* dst, int width, int global_height, int buf_y0,
+                         int buf_rows, int out_y0, int out_rows, int64_t guide_stride, int64_t src_stride,
+                         int64_t dst_stride, int r, float eps, int border, void* stream)
+{
+    if (buf_rows <= 0 || buf_y0 < 0 || buf_y0 + buf_rows > global_height) return fail(GF_ERR_INVALID, "buffer rows outside the image");
+    Job j = strip_job(guide, src, dst, width, global_height, buf_y0, buf_rows, out_y0, out_rows, guide_stride, src_stride, dst_stride, r, eps,
+                      border, stream);
     return run_jobs(&j, 1);
 }
 
@@ -689,6 +697,26 @@ __global__ void __launch_bounds__(256) gf_halo_pull_kernel(const GfHaloPullArgs 
     if (g.vec4) {
         const int w4 = g.width >> 2;
         const int64_t n = (int64_t)rows * w4;
+        if (n < (1ll << 31)) {
+            // NVLink reads have ~3 us of latency: U independent 16-byte loads per thread before the first store keep
+            // the whole region in flight (one load per thread and trip measured 409 GB/s on 16 MiB)
+            constexpr int U = 8;
+            const unsigned nt = gridDim.x * blockDim.x, n32 = (unsigned)n;
+            for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n32; i0 += U * nt) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned i = i0 + u * nt;
+                    if (i < n32) { const unsigned y = i / (unsigned)w4, x = i - y * (unsigned)w4; v[u] = reinterpret_cast<const float4*>(s + y * ss)[x]; }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned i = i0 + u * nt;
+                    if (i < n32) { const unsigned y = i / (unsigned)w4, x = i - y * (unsigned)w4; reinterpret_cast<float4*>(d + y * ds)[x] = v[u]; }
+                }
+            }
+            return;
+        }
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
             const int y = (int)(i / w4), x = (int)(i - (int64_t)y * w4);
             reinterpret_cast<float4*>(d + y * ds)[x] = reinterpret_cast<const float4*>(s + y * ss)[x];
@@ -704,6 +732,33 @@ __global__ void __launch_bounds__(256) gf_halo_pull_kernel(const GfHaloPullArgs 
 #endif
 
 // ---- row strips with the halo exchange inside the call (gf_run_strips) ------------------------
+#ifndef GF_CPU_EMU
+namespace {
+// one side stream + fork/join events per device for the interior bands of gf_run_strips; the lock covers the enqueue
+struct StripSide {
+    std::mutex mu;
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool init = false;
+};
+StripSide g_strip_side[64];
+std::mutex g_strip_side_mu;
+StripSide* strip_side()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    StripSide* sd = &g_strip_side[dev];
+    std::lock_guard<std::mutex> lock(g_strip_side_mu);
+    if (!sd->init) {
+        if (cudaStreamCreateWithFlags(&sd->s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&sd->e0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&sd->e1, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        sd->init = true;
+    }
+    return sd;
+}
+}  // namespace
+#endif
 static void strip_halo_rows(int global_height, int y0, int rows, int r, int* top, int* bot)
 {
     *top = y0 > 0 ? (2 * r < y0 ? 2 * r : y0) : 0;
@@ -733,11 +788,10 @@ int gf_run_strips(float* guide_buf, float* src_buf, float* dst, int width, int g
     // the numbers come from the geometry, not from what a neighbour says about itself)
     if ((up && top > 0 && up->rows < top) || (down && bot > 0 && down->rows < bot))
         return fail(GF_ERR_INVALID, "gf_run_strips: a neighbour strip is shorter than the %d-row halo it must supply", 2 * r);
-#ifndef GF_CPU_EMU
     // ONE small kernel pulls all four halo regions (2 planes x 2 neighbours) straight out of the peers' memory with
     // 16-byte loads over NVLink.  Measured at 8 GPUs (32768^2, r=16, 16 MiB of halos per rank): four cudaMemcpy2DAsync
     // cost 0.061 ms back to back on the stream and 0.063 ms on four side streams (copy-engine set-up and cross-stream
-    // events, not bandwidth) -- the difference between 6.8x and 7x on BASELINE configs[4].
+    // events, not bandwidth), the pull kernel 0.041 ms.
     GfHaloPullArgs pa;
     int nreg = 0;
     auto add = [&](float* dst_rows, int64_t dstride, const float* peer, int64_t pstride, int first_row, int n) {
@@ -758,7 +812,9 @@ int gf_run_strips(float* guide_buf, float* src_buf, float* dst, int width, int g
         add(guide_buf + off * gs, gs, down->guide, down->guide_stride, down->top, bot);
         add(src_buf + off * ss, ss, down->src, down->src_stride, down->top, bot);
     }
-    if (nreg > 0) {
+    auto pull = [&](void* on) -> int {
+        if (nreg == 0) return GF_OK;
+#ifndef GF_CPU_EMU
         for (int i = nreg; i < 4; ++i) { pa.dst[i] = nullptr; pa.src[i] = nullptr; pa.dstride[i] = pa.sstride[i] = 0; pa.rows[i] = 0; }
         pa.width = width;
         bool v4 = (width & 3) == 0;
@@ -769,20 +825,64 @@ int gf_run_strips(float* guide_buf, float* src_buf, float* dst, int width, int g
         gf_rt_device_info(&sms, &mj, &mn);
         dim3 grid(sms, nreg), block(256);
         auto k = gf_halo_pull_kernel;
-        GF_LAUNCH(k, grid, block, 0, stream, pa);
+        GF_LAUNCH(k, grid, block, 0, on, pa);
         if (const char* le = gf_rt_launch_error()) return fail(GF_ERR_CUDA, "gf_run_strips: halo pull kernel: %s", le);
         g_launches++;
-    }
 #else
-    auto pull = [&](float* dst_rows, int64_t dstride, const float* peer, int64_t pstride, int first_row, int n) {
-        const int64_t ps = pstride > 0 ? pstride : width;
-        for (int y = 0; y < n; ++y) std::memcpy(dst_rows + y * dstride, peer + (int64_t)(first_row + y) * ps, (size_t)width * sizeof(float));
-    };
-    if (up && top > 0) { const int first = up->top + up->rows - top; pull(guide_buf, gs, up->guide, up->guide_stride, first, top); pull(src_buf, ss, up->src, up->src_stride, first, top); }
-    if (down && bot > 0) { const int64_t off = (int64_t)(top + rows); pull(guide_buf + off * gs, gs, down->guide, down->guide_stride, down->top, bot); pull(src_buf + off * ss, ss, down->src, down->src_stride, down->top, bot); }
+        for (int i = 0; i < nreg; ++i)
+            for (int y = 0; y < pa.rows[i]; ++y)
+                std::memcpy(pa.dst[i] + y * pa.dstride[i], pa.src[i] + y * pa.sstride[i], (size_t)width * sizeof(float));
 #endif
-    return gf_guided_gray_strip(guide_buf, src_buf, dst, width, global_height, y0 - top, top + rows + bot, y0, rows, gs, ss, dst_stride, r, eps,
-                                border, stream);
+        return GF_OK;
+    };
+    Job j = strip_job(guide_buf, src_buf, dst, width, global_height, y0 - top, top + rows + bot, y0, rows, gs, ss, dst_stride, r, eps, border, stream);
+    // OPTION GF_STRIP_OVERLAP=1 (off by default: measured slower): exchange off the critical path.  Only the first and the
+    // last 2r OUTPUT rows of the strip read halo rows, so the strip is filtered in three jobs: rows [2r, rows-2r) on the
+    // caller's stream at once; the pull and then the two 2r-row seam jobs on a side stream.
+    // Measured (32768-column strips of 4096 rows, r = 16; profiles/r2_strip_overlap_8gpu.jsonl, r2_strip_phases.jsonl):
+    //   8 GPUs   pull-then-launch 0.967 ms   this option 0.992 ms
+    //   1 GPU, neighbours faked on the same GPU: main job alone 0.913 ms, both seam jobs alone 0.099 ms, main + seams
+    //   together 0.947 ms, everything 0.956 ms, against 0.932 ms for pull-then-launch.
+    // The seam jobs pay a 4r-row ramp for 2r output rows (4.5 % more row iterations), and the slots the main job leaves
+    // idle (s8_r16 keeps 4 warps per SM: 171 column strips x 3 bands = 513 of 592) are not free: a fourth warp on an SM
+    // slows the other three (profiles/r2_s8_residency.jsonl), so hiding a 0.02-0.04 ms pull costs 0.034 ms.  The other
+    // split that was tried -- first and last BAND of every column strip after the pull, the middle bands before it --
+    // lost by more (1.02-1.04 ms): with 3 bands per strip two of them wait for the pull.
+    const int cut_top = (up && top > 0) ? 2 * r : 0, cut_bot = (down && bot > 0) ? 2 * r : 0;
+    const int min_main = GF_KNOB("GF_STRIP_MIN_MAIN_ROWS", 16 * r + 64);
+    if (nreg > 0 && GF_KNOB("GF_STRIP_OVERLAP", 0) && rows - cut_top - cut_bot >= min_main && check_common(j) == GF_OK &&
+        !overlaps(j.dst, j.guide, j.buf_rows, 1) && !overlaps(j.dst, j.src, j.buf_rows, 1)) {
+        const int64_t dstr = or_packed(dst_stride, width, 1);
+        void* side = stream;
+#ifndef GF_CPU_EMU
+        StripSide* sd = strip_side();
+        if (!sd) return fail(GF_ERR_CUDA, "gf_run_strips: side stream");
+        std::lock_guard<std::mutex> lock(sd->mu);
+        side = sd->s;
+        if (cudaEventRecord(sd->e0, (cudaStream_t)stream) != cudaSuccess || cudaStreamWaitEvent(sd->s, sd->e0, 0) != cudaSuccess)
+            return fail(GF_ERR_CUDA, "gf_run_strips: fork");
+#endif
+        auto part = [&](int first, int n, void* on) -> int {       // output rows [first, first + n) of the strip
+            if (n <= 0) return GF_OK;
+            Job p = j;
+            p.out_y0 = y0 + first; p.out_rows = n; p.stream = on;
+            p.dst.ptr = dst + (int64_t)first * dstr;
+            return run_jobs(&p, 1);
+        };
+        const int skip = GF_KNOB("GF_STRIP_DEBUG_SKIP", 0);      // measurement only (wrong pixels): 1 no main job, 2 no pull, 4 no seam jobs
+        int rc = (skip & 1) ? GF_OK : part(cut_top, rows - cut_top - cut_bot, stream);
+        if (rc == GF_OK && !(skip & 2)) rc = pull(side);
+        if (rc == GF_OK && !(skip & 4)) rc = part(0, cut_top, side);
+        if (rc == GF_OK && !(skip & 4)) rc = part(rows - cut_bot, cut_bot, side);
+#ifndef GF_CPU_EMU
+        // join even after an error: the caller's stream must not run ahead of what was already queued on the side stream
+        if (cudaEventRecord(sd->e1, sd->s) != cudaSuccess || cudaStreamWaitEvent((cudaStream_t)stream, sd->e1, 0) != cudaSuccess)
+            return rc ? rc : fail(GF_ERR_CUDA, "gf_run_strips: join");
+#endif
+        return rc;
+    }
+    if (int rc = pull(stream)) return rc;
+    return run_jobs(&j, 1);
 }
 
 // device allocations that can be shared with the other ranks of a node (CUDA IPC needs allocation base pointers)

@@ -406,6 +406,24 @@ def test_run_strips_pulls_halos(be, world, border):
     assert np.abs(q - O.guided_filter_gray(I, p, 3, 1e-2, border, np.float64)).max() <= TOL
 
 
+@pytest.mark.parametrize("border", [0, 1, 2])
+def test_run_strips_exchange_behind_the_kernel(be, border, knob):
+    """gf_run_strips with GF_STRIP_OVERLAP=1: rows that read no halo are filtered at once, the 2r seam rows at either
+    end after the pull (three jobs instead of one) -- same result as the single image and as pull-then-launch."""
+    knob(be, "GF_STRIP_OVERLAP", 1)
+    knob(be, "GF_STRIP_MIN_MAIN_ROWS", 16)       # the 80-row strips of this test count as tall
+    I, p = synth_pair(240, 512, seed=93, kind="structured")
+    n0 = be.api.launch_count()
+    q = be.run_strips(I, p, 3, 4, 1e-2, border)
+    assert be.api.launch_count() - n0 == 7       # (main + seam) + (main + 2 seams) + (main + seam); the emulator's pull is a memcpy
+    assert np.abs(q - O.guided_filter_gray(I, p, 4, 1e-2, border, np.float64)).max() <= TOL
+    knob(be, "GF_STRIP_OVERLAP", 0)              # the sequential form: pull, then one launch
+    n0 = be.api.launch_count()
+    q1 = be.run_strips(I, p, 3, 4, 1e-2, border)
+    assert be.api.launch_count() - n0 == 3
+    assert np.abs(q - q1).max() <= 1e-5          # different band boundaries: running sums round differently
+
+
 def test_run_strips_rejects_short_neighbours(be):
     I, p = synth_pair(40, 64, seed=92)
     with pytest.raises(Exception, match="shorter than"):
