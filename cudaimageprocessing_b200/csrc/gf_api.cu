@@ -446,8 +446,9 @@ static int integral_entry(const unsigned char* src, T* integral, T* scratch, int
     if (ss <= 0) ss = sw;
     if (ds <= 0) ds = w;
     if (ss < sw || ds < w) return fail(GF_ERR_INVALID, "%s: row stride smaller than a row", name);
-    if (const char* e = gf_sat_launch<T>(src, integral, scratch, sw, sh, w, h, ss, ds, stream)) return fail(GF_ERR_CUDA, "%s: %s", name, e);
-    g_launches += 3;
+    int launches = 0;
+    if (const char* e = gf_sat_launch<T>(src, integral, scratch, sw, sh, w, h, ss, ds, stream, &launches)) return fail(GF_ERR_CUDA, "%s: %s", name, e);
+    g_launches += launches;
     g_kernel = sizeof(T) == 4 ? "integral_i32" : "integral_i64";
     return GF_OK;
 }

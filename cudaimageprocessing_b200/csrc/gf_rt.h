@@ -28,6 +28,8 @@ static inline const char* gf_rt_device_info(int* sms, int* major, int* minor) { 
 static inline size_t gf_rt_max_smem() { return 200 * 1024; }
 #else
 #include <cuda_runtime.h>
+
+#include <mutex>
 #define GF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__)
 static inline const char* gf_rt_launch_error()
 {
@@ -47,9 +49,37 @@ template <class K> static inline int gf_rt_ctas_per_sm(K kernel, int threads, si
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
     return n;
 }
+// Stream-ordered temporaries come from a pool of the library's own (one per device) that keeps up to 256 MiB cached:
+// the default pool returns everything to the driver at every synchronisation (release threshold 0), which turns the
+// first temporary after each cudaDeviceSynchronize into a driver allocation.
+inline cudaMemPool_t gf_rt_pool()
+{
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    static bool failed[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev] && !failed[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) {
+            pools[dev] = nullptr; failed[dev] = true;
+            cudaGetLastError();
+        } else {
+            uint64_t keep = 256ull << 20;
+            cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    return pools[dev];
+}
 static inline const char* gf_rt_alloc_async(void** p, size_t n, void* stream)
 {
-    cudaError_t e = cudaMallocAsync(p, n, (cudaStream_t)stream);
+    cudaMemPool_t pool = gf_rt_pool();
+    cudaError_t e = pool ? cudaMallocFromPoolAsync(p, n, pool, (cudaStream_t)stream) : cudaMallocAsync(p, n, (cudaStream_t)stream);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 static inline void gf_rt_free_async(void* p, void* stream) { cudaFreeAsync(p, (cudaStream_t)stream); }

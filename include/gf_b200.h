@@ -203,8 +203,9 @@ int gf_guided_gray_u8(const unsigned char* guide, const unsigned char* src, unsi
    integral[y*dst_stride + x] = sum of src over rows <= y and columns <= x (inclusive, W x H).
    Strides in ELEMENTS.  The int32 form wraps modulo 2^32 exactly like the reference's int
    accumulators; the int64 form never overflows (use it above 8.4 Mpix).  `scratch` (optional):
-   at least ceil(height/16) * width elements -- the reference's w*h `buff` is always enough;
-   NULL = stream-ordered temporary.  The padded form writes a dst_width x dst_height table
+   at least ceil(height/16) * width elements -- the reference's w*h `buff` is always enough; used
+   when the per-band / per-strip carries fit, else (and when NULL) they live in a stream-ordered
+   temporary.  The padded form writes a dst_width x dst_height table
    (>= the source size, e.g. aligned to 4) of the zero-extended image. */
 int gf_integral_u8_i32(const unsigned char* src, int32_t* integral, int32_t* scratch, int width, int height,
                        int64_t src_stride, int64_t dst_stride, void* stream);

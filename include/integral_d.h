@@ -1,7 +1,7 @@
 // integral_d.h -- drop-in for the reference's Integral/integral_d.h:5-8 (the two integral-image
 // launchers; its curand/compare helpers hInitRand, hRandFill, hCmpMaxAbsDiff are demo utilities of
 // Integral/main.cpp and are not part of this library).  Same signatures, forwarded to libgf_b200.so.
-// Differences a caller can observe: `buff` is only used as scratch for per-band column totals (any
+// Differences a caller can observe: `buff` is only used as scratch for the per-band / per-strip carries (any
 // w*h-int buffer as in Integral/main.cpp:52 is large enough; it may be NULL); calls are asynchronous
 // on the default stream like the reference's.
 #pragma once

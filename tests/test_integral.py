@@ -67,6 +67,23 @@ def test_integral_emulated(shape):
     assert np.array_equal(out, O.integral_u8(ext, np.int32))
 
 
+@pytest.mark.parametrize("opts", [{"GF_SAT_TWO_PASS": 0}, {"GF_SAT_TWO_PASS": 0, "GF_SAT_HB": 3}, {"GF_SAT_TWO_PASS": 0, "GF_SAT_HB": 1000},
+                                  {"GF_SAT_TWO_PASS": 1}, {"GF_SAT_TWO_PASS": 1, "GF_SAT_HB": 5}])
+def test_integral_emulated_forms(opts):
+    """both forms forced (reduce-then-scan / two-pass; the library picks by size and type), many short bands, one band"""
+    api, up, down = _emu()
+    for k, v in opts.items():
+        api.set_option(k, v)
+    try:
+        for shape in ((70, 520), (33, 300), (19, 8)):
+            img = np.random.default_rng(sum(shape)).integers(0, 256, shape, dtype=np.uint8)
+            assert np.array_equal(_run(api, up, down, img), O.integral_u8(img, np.int32))
+            assert np.array_equal(_run(api, up, down, img, i64=True, with_scratch=True), O.integral_u8(img, np.int64))
+    finally:
+        for k in opts:
+            api.set_option(k, -1)
+
+
 def _cuda():
     import torch
     if not torch.cuda.is_available():
@@ -110,3 +127,19 @@ def test_integral_gpu_overflow_and_int64():
     assert np.array_equal(_run(api, up, down, img), O.integral_u8(img, np.int32))
     out = _run(api, up, down, img, i64=True)
     assert out[-1, -1] == 255 * 3000 * 3000 and np.array_equal(out, O.integral_u8(img, np.int64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("two_pass", [0, 1])
+def test_integral_gpu_both_forms(two_pass):
+    """the reduce-then-scan form and the two-pass form, each forced, on an aligned 4K table, an unaligned one and the
+    int64 table (the library chooses between them by size and type: csrc/gf_integral.cuh, gf_sat_launch)."""
+    api, up, down = _cuda()
+    api.set_option("GF_SAT_TWO_PASS", two_pass)
+    try:
+        for shape in ((2160, 3840), (2161, 3001)):
+            img = np.random.default_rng(shape[1]).integers(0, 256, shape, dtype=np.uint8)
+            assert np.array_equal(_run(api, up, down, img), O.integral_u8(img, np.int32))
+            assert np.array_equal(_run(api, up, down, img, i64=True, with_scratch=True), O.integral_u8(img, np.int64))
+    finally:
+        api.set_option("GF_SAT_TWO_PASS", -1)
