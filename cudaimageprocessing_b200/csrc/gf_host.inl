@@ -99,9 +99,27 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
     // 8: 1.75, 16: 1.65 -- chunked copies lose duplex efficiency, so few large bands win (ideal duplex: 1.27 ms)
     nb = nb < 1 ? 1 : (nb > 4 ? 4 : nb);
     nb = GF_KNOB("GF_HOST_BANDS", nb); nb = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
+    // band b is taper % as tall as band b-1: what stays exposed at the end is the kernel and the download of the LAST band.
+    // Measured (4K frame, profiles/r2_e2e_bands_taper.jsonl): 4 uniform bands 1.60 ms, taper 80 %: 1.57, 65 %: 1.54,
+    // 50-55 %: 1.50, 35 %: 1.54, 25 %: 1.62 (1 band, no overlap: 1.87; upload alone ~1.2).
+    int taper = GF_KNOB("GF_HOST_TAPER_PCT", 50);
+    taper = taper < 20 ? 20 : (taper > 100 ? 100 : taper);
+    int cut[kMaxBands + 1];
+    {
+        double wsum = 0.0, w = 1.0, acc = 0.0;
+        for (int b = 0; b < nb; ++b) { wsum += w; w *= taper / 100.0; }
+        w = 1.0;
+        cut[0] = 0;
+        for (int b = 0; b < nb; ++b) {
+            acc += w; w *= taper / 100.0;
+            cut[b + 1] = b == nb - 1 ? height : (int)(height * (acc / wsum));
+            if (cut[b + 1] < cut[b]) cut[b + 1] = cut[b];
+        }
+    }
     int up_to = 0;
     for (int b = 0; b < nb; ++b) {
-        const int y0 = (int)((int64_t)height * b / nb), y1 = (int)((int64_t)height * (b + 1) / nb);
+        const int y0 = cut[b], y1 = cut[b + 1];
+        if (y1 <= y0) continue;
         int need = y1 + 2 * r;
         if (need > height || b == nb - 1) need = height;
         if (need > up_to) {

@@ -393,6 +393,19 @@ def test_box_filter(be, c):
     assert np.abs(be.box(a, 7, 1, inplace=True) - O.box_mean(a, 7, 1)).max() <= 2e-6
 
 
+@pytest.mark.parametrize("bands,taper", [(1, 100), (4, 100), (4, 50), (8, 25), (16, 20)])
+def test_host_entry_band_pipeline(be, knob, bands, taper):
+    """gf_guided_gray_host over the pipeline's band count and taper (band b is taper % as tall as band b-1; very thin
+    and empty bands included), pageable host buffers, all three borders on a frame with an odd width."""
+    knob(be, "GF_HOST_BANDS", bands)
+    knob(be, "GF_HOST_TAPER_PCT", taper)
+    for (h, w, r, border) in ((401, 517, 8, 0), (300, 512, 4, 1), (97, 1030, 3, 2)):
+        I, p = synth_pair(h, w, seed=14 + border)
+        q = np.full_like(I, np.nan)
+        be.api.call("gf_guided_gray_host", I.ctypes.data, p.ctypes.data, q.ctypes.data, w, h, r, 1e-2, border)
+        assert np.abs(q - C.guided_gray_f64(I, p, r, 1e-2, border, NT)).max() <= TOL
+
+
 def test_host_entry_and_dropin_program(be, tmp_path):
     """gf_guided_gray_host (the e2e call) and the C++ program written against the reference's
     headers (tests/dropin/dropin_demo.cpp) produce the oracle's answer."""
