@@ -232,6 +232,11 @@ def main():
     api = pkg.api()
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)
+    # host side of the e2e leg: this rank's pinned buffers belong on the NUMA node of its GPU
+    numa_cpus = None
+    if world > 1 and not os.environ.get("GF_BENCH_NO_BIND"):
+        from cudaimageprocessing_b200 import dist as gfdist
+        numa_cpus = gfdist.bind_host_to_gpu(local_rank)
 
     host = synth_frames(NSETS)
     frames = []
@@ -372,7 +377,8 @@ def main():
                      "algorithmic_bytes_per_px": ALG_BYTES_PER_PX},
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes,
                 "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3, "matches_device_path": e2e_ok,
-                "api": "gf_guided_gray_host (pinned host buffers)", "pageable": e2e_pageable},
+                "api": "gf_guided_gray_host (pinned host buffers)", "pageable": e2e_pageable,
+                "host_cores_bound": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else None)},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

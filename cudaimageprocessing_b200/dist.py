@@ -21,6 +21,42 @@ import torch
 import torch.distributed as dist
 
 
+def bind_host_to_gpu(device_index: int):
+    """Pins the calling process to the CPU cores next to GPU `device_index` (its NUMA node), so that pinned host buffers
+    allocated afterwards (first touch) sit on the memory controller the GPU's PCIe root hangs off.  One process per GPU
+    under torchrun otherwise runs wherever the scheduler puts it, and uploads from the far socket cross the CPU
+    interconnect.  Returns the core list, or None when neither NVML nor sysfs knows it (nothing is changed then)."""
+    import os
+    cpus = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+    except Exception:
+        cpus = None
+    if not cpus:
+        try:
+            bdf = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+            if bdf:
+                txt = open(f"/sys/bus/pci/devices/{bdf.lower()}/local_cpulist").read().strip()
+                cpus = []
+                for part in txt.split(","):
+                    a, _, b = part.partition("-")
+                    cpus += list(range(int(a), int(b or a) + 1))
+        except Exception:
+            cpus = None
+    if not cpus:
+        return None
+    allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+    if not allowed:
+        return None
+    os.sched_setaffinity(0, allowed)
+    return allowed
+
+
 def shard_frames(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous block of frames for `rank` (sizes differ by at most one)."""
     base, rem = divmod(n_frames, world)

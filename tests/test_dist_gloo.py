@@ -83,3 +83,13 @@ def test_strip_too_short_is_refused():
     from cudaimageprocessing_b200 import dist as D
     assert D.halo_rows(100, 0, 4, 8) == (0, 16) and D.halo_rows(100, 3, 4, 8) == (16, 0)
     assert D.strip_rows(10, 1, 3) == (3, 6)
+
+
+def test_bind_host_to_gpu_without_a_gpu_changes_nothing():
+    """bind_host_to_gpu (bench.py, N > 1) must leave the process alone when neither NVML nor sysfs knows the GPU"""
+    import os
+    from cudaimageprocessing_b200 import dist as D
+    before = os.sched_getaffinity(0)
+    cpus = D.bind_host_to_gpu(0)
+    after = os.sched_getaffinity(0)
+    assert cpus is None and after == before or (cpus is not None and set(cpus) == after and after <= before)
