@@ -7,17 +7,17 @@ import cudaimageprocessing_b200 as pkg
 api = pkg.api()
 
 def run(I, p, r, env=None):
-    for k, v in (env or {}).items(): os.environ[k] = str(v)
+    for k, v in (env or {}).items(): api.set_option(k, int(v))
     n, h, w = p.shape
     q = torch.full_like(p, float("nan"))
     api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q.data_ptr(), n, w, h, 3, 0, 0, 0, 0, 0, 0, r, 1e-2, 0, None)
     torch.cuda.synchronize()
     k = api.last_kernel()
-    for kk in (env or {}): os.environ.pop(kk, None)
+    for kk in (env or {}): api.set_option(kk, -1)
     return q, k
 
 def timeit(I, p, r, iters=5, env=None):
-    for k, v in (env or {}).items(): os.environ[k] = str(v)
+    for k, v in (env or {}).items(): api.set_option(k, int(v))
     n, h, w = p.shape
     q = torch.empty_like(p)
     s = torch.cuda.current_stream(); sp = ctypes.c_void_p(s.cuda_stream)
@@ -29,7 +29,7 @@ def timeit(I, p, r, iters=5, env=None):
     e1.record(s); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     k = api.last_kernel()
-    for kk in (env or {}): os.environ.pop(kk, None)
+    for kk in (env or {}): api.set_option(kk, -1)
     return {"frames": n, "w": w, "h": h, "r": r, "kernel": k, "ms": round(ms, 3), "gpix_s": round(n * w * h / ms / 1e6, 2),
             "gbs_alg": round(20.0 * n * w * h / ms / 1e6, 1), "env": env or {}}
 

@@ -8,7 +8,7 @@ api = pkg.api()
 s = torch.cuda.current_stream(); sp = ctypes.c_void_p(s.cuda_stream)
 
 def timeit(I, p, q, r, iters, env):
-    for k, v in env.items(): os.environ[k] = str(v)
+    for k, v in env.items(): api.set_option(k, int(v))
     n, h, w = p.shape
     f = lambda: api.call("gf_guided_batch", I.data_ptr(), p.data_ptr(), q.data_ptr(), n, w, h, 3, 0, 0, 0, 0, 0, 0, r, 1e-2, 0, sp)
     f(); f(); torch.cuda.synchronize()
@@ -16,7 +16,7 @@ def timeit(I, p, q, r, iters, env):
     e0.record(s)
     for _ in range(iters): f()
     e1.record(s); torch.cuda.synchronize()
-    for k in env: os.environ.pop(k, None)
+    for k in env: api.set_option(k, -1)
     return e0.elapsed_time(e1) / iters
 
 g = torch.Generator(device="cuda").manual_seed(0)

@@ -10,7 +10,7 @@ for (w, h, r, sig) in [(3840, 2160, 8, 3.0), (3840, 2160, 4, 1.5), (3840, 2160, 
     sets = [(torch.rand((h, w), device="cuda"), torch.empty((h, w), device="cuda")) for _ in range(6)]
     row = {"w": w, "h": h, "r": r}
     for hb in (0, 16, 24, 32, 40, 48, 64, 72, 96, 128, 192, 270):
-        if hb: os.environ["GF_GAUSS_HB"] = str(hb)
+        if hb: api.set_option("GF_GAUSS_HB", int(hb))
         i = [0]
         def f():
             a, b = sets[i[0] % 6]; i[0] += 1
@@ -21,7 +21,7 @@ for (w, h, r, sig) in [(3840, 2160, 8, 3.0), (3840, 2160, 4, 1.5), (3840, 2160, 
         e0.record(s)
         for _ in range(40): f()
         e1.record(s); torch.cuda.synchronize()
-        os.environ.pop("GF_GAUSS_HB", None)
+        api.set_option("GF_GAUSS_HB", -1)
         row["default" if not hb else f"hb{hb}"] = round(e0.elapsed_time(e1) / 40 * 1e3, 2)
     print(json.dumps(row), flush=True)
     del sets

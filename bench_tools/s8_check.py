@@ -30,14 +30,14 @@ def emit(o):
 
 def run_gray(I, p, r, eps, border, env=None):
     for k, v in (env or {}).items():
-        os.environ[k] = str(v)
+        api.set_option(k, int(v))
     h, w = I.shape
     q = torch.full_like(I, float("nan"))
     api.call("gf_guided_gray", I.data_ptr(), p.data_ptr(), q.data_ptr(), None, None, w, h, 0, 0, 0, 0, r, eps, border, None)
     torch.cuda.synchronize()
     k = api.last_kernel()
     for kk in (env or {}):
-        os.environ.pop(kk, None)
+        api.set_option(kk, -1)
     return q, k
 
 

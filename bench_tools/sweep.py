@@ -19,7 +19,7 @@ api = pkg.api()
 
 def time_gray(w, h, r, nsets=6, iters=60, border=0, env=None):
     for k, v in (env or {}).items():
-        os.environ[k] = str(v)
+        api.set_option(k, int(v))
     g = torch.Generator(device="cuda").manual_seed(0)
     sets = [(torch.rand((h, w), device="cuda", generator=g), torch.rand((h, w), device="cuda", generator=g),
              torch.empty((h, w), device="cuda")) for _ in range(nsets)]
@@ -40,7 +40,7 @@ def time_gray(w, h, r, nsets=6, iters=60, border=0, env=None):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     for k in (env or {}):
-        os.environ.pop(k, None)
+        api.set_option(k, -1)
     return {"w": w, "h": h, "r": r, "kernel": api.last_kernel(), "us": ms * 1e3, "gpix_s": w * h / ms / 1e6,
             "gbs_alg": 12.0 * w * h / ms / 1e6, "env": env or {}}
 

@@ -10,11 +10,11 @@ s = torch.cuda.current_stream(); sp = ctypes.c_void_p(s.cuda_stream)
 
 
 def setenv(env):
-    for k, v in env.items(): os.environ[k] = str(v)
+    for k, v in env.items(): api.set_option(k, int(v))
 
 
 def clrenv(env):
-    for k in env: os.environ.pop(k, None)
+    for k in env: api.set_option(k, -1)
 
 
 def timed(f, iters):

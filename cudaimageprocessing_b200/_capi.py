@@ -38,6 +38,8 @@ SIGNATURES = {
     "gf_linear_transform": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, P]),
     "gf_guided_gray_host": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int]),
     "gf_host_alloc": (c_int, [P, c_size_t]),
+    "gf_host_register": (c_int, [P, c_size_t]),
+    "gf_host_unregister": (c_int, [P]),
     "gf_host_free": (c_int, [P]),
     "gf_guided_gray_u8": (c_int, [P, P, P, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_float, c_int, P]),
     "gf_gaussian_gray": (c_int, [P, P, c_int, c_int, c_int64, c_int64, c_int, ctypes.c_double, P]),

@@ -9,6 +9,8 @@
 extern "C" {
 int gf_host_alloc(void** ptr, size_t bytes) { *ptr = std::malloc(bytes); return *ptr ? GF_OK : fail(GF_ERR_NOMEM, "malloc"); }
 int gf_host_free(void* ptr) { std::free(ptr); return GF_OK; }
+int gf_host_register(void* ptr, size_t) { return ptr ? GF_OK : fail(GF_ERR_INVALID, "null pointer"); }
+int gf_host_unregister(void* ptr) { return ptr ? GF_OK : fail(GF_ERR_INVALID, "null pointer"); }
 int gf_guided_gray_host(const float* guide, const float* src, float* dst, int width, int height, int r, float eps, int border)
 {
     return gf_guided_gray(guide, src, dst, nullptr, nullptr, width, height, 0, 0, 0, 0, r, eps, border, nullptr);
@@ -62,6 +64,20 @@ int gf_host_alloc(void** ptr, size_t bytes)
 int gf_host_free(void* ptr)
 {
     GF_CU(cudaFreeHost(ptr));
+    return GF_OK;
+}
+
+int gf_host_register(void* ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0) return fail(GF_ERR_INVALID, "null pointer");
+    GF_CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return GF_OK;
+}
+
+int gf_host_unregister(void* ptr)
+{
+    if (!ptr) return fail(GF_ERR_INVALID, "null pointer");
+    GF_CU(cudaHostUnregister(ptr));
     return GF_OK;
 }
 

@@ -406,6 +406,23 @@ def test_host_entry_band_pipeline(be, knob, bands, taper):
         assert np.abs(q - C.guided_gray_f64(I, p, r, 1e-2, border, NT)).max() <= TOL
 
 
+def test_host_entry_registered_buffers(be):
+    """gf_host_register pins a caller's own (malloc'd) buffers in place; the host call gives the same pixels"""
+    I, p = synth_pair(1080, 1920, seed=17)
+    q0, q1 = np.empty_like(I), np.empty_like(I)
+    be.api.call("gf_guided_gray_host", I.ctypes.data, p.ctypes.data, q0.ctypes.data, 1920, 1080, 8, 1e-2, 0)
+    for a in (I, p, q1):
+        be.api.call("gf_host_register", a.ctypes.data, a.nbytes)
+    try:
+        be.api.call("gf_guided_gray_host", I.ctypes.data, p.ctypes.data, q1.ctypes.data, 1920, 1080, 8, 1e-2, 0)
+    finally:
+        for a in (I, p, q1):
+            be.api.call("gf_host_unregister", a.ctypes.data)
+    assert np.array_equal(q0, q1)
+    with pytest.raises(Exception):
+        be.api.call("gf_host_unregister", I.ctypes.data)        # not registered any more
+
+
 def test_host_entry_and_dropin_program(be, tmp_path):
     """gf_guided_gray_host (the e2e call) and the C++ program written against the reference's
     headers (tests/dropin/dropin_demo.cpp) produce the oracle's answer."""
