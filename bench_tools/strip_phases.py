@@ -1,7 +1,11 @@
 """Developer tool (ONE GPU): the parts of gf_run_strips on a BASELINE configs[4] strip (32768 x 4096, r=16) with both
 neighbours faked by buffers on the same GPU -- what the main job, the pull and the seam jobs cost alone and together.
 
-    python bench_tools/strip_phases.py > gpurun_out/strip_phases.jsonl"""
+    python bench_tools/strip_phases.py > gpurun_out/strip_phases.jsonl
+
+The "overlap_*_only" / "no_pull" settings need a library built with -DGF_STRIP_DEBUG (build.build_variant("libgf_strip_debug.so",
+["-DGF_STRIP_DEBUG"]) and GF_LIB_PATH): the product library ignores GF_STRIP_DEBUG_SKIP, because skipping parts gives
+wrong pixels."""
 import ctypes
 import json
 import os

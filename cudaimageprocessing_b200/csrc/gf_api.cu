@@ -870,7 +870,11 @@ int gf_run_strips(float* guide_buf, float* src_buf, float* dst, int width, int g
             p.dst.ptr = dst + (int64_t)first * dstr;
             return run_jobs(&p, 1);
         };
-        const int skip = GF_KNOB("GF_STRIP_DEBUG_SKIP", 0);      // measurement only (wrong pixels): 1 no main job, 2 no pull, 4 no seam jobs
+#ifdef GF_STRIP_DEBUG   // timing builds only (bench_tools/strip_phases.py): parts can be left out, the pixels are then WRONG
+        const int skip = GF_KNOB("GF_STRIP_DEBUG_SKIP", 0);      // 1 no main job, 2 no pull, 4 no seam jobs
+#else
+        const int skip = 0;
+#endif
         int rc = (skip & 1) ? GF_OK : part(cut_top, rows - cut_top - cut_bot, stream);
         if (rc == GF_OK && !(skip & 2)) rc = pull(side);
         if (rc == GF_OK && !(skip & 4)) rc = part(0, cut_top, side);
