@@ -3,7 +3,11 @@
 // gf_guided_gray_host is the end-to-end call: it uploads guide and src, filters, and downloads
 // dst, pipelined in row bands over three streams so that H2D of band b+1, the kernel of band b
 // and D2H of band b-1 overlap (PCIe is full duplex; the kernel is ~1% of the copy time).
+#include <condition_variable>
+#include <cstring>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #ifdef GF_CPU_EMU
 extern "C" {
@@ -27,7 +31,9 @@ struct HostPipe {
     float* dev = nullptr;      // guide | src | dst planes
     size_t cap = 0;            // floats per plane
     cudaStream_t up = nullptr, comp = nullptr, down = nullptr;
-    cudaEvent_t ev_up[kMaxBands], ev_k[kMaxBands];
+    cudaEvent_t ev_up[kMaxBands], ev_k[kMaxBands], ev_down[kMaxBands];
+    float* pin = nullptr;      // PAGEABLE callers only: pinned guide | src | dst planes the copies are staged through
+    size_t pin_cap = 0;
     bool init = false;
 };
 HostPipe g_pipes[kMaxDevices];
@@ -43,6 +49,72 @@ HostPipe g_pipes[kMaxDevices];
         cudaError_t e_ = (call);                                                     \
         if (e_ != cudaSuccess) { drain(P); return fail(GF_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } \
     } while (0)
+
+// Pageable host buffers (cv::Mat data, main.cpp:229-230): cudaMemcpyAsync from pageable memory is a single-threaded
+// staged copy inside the driver (4K frame: 6.9 ms against 1.5 ms from pinned memory).  The host call stages such
+// buffers itself: a few threads copy each row band between the caller's memory and pinned planes while the DMA engine
+// moves the previous band (profiles/r2_e2e_pageable_staged.jsonl).
+class CopyPool {
+public:
+    static CopyPool& get() { static CopyPool* p = new CopyPool(); return *p; }     // never destroyed: workers outlive main()
+    void copy(void* d, const void* s, size_t n, int threads)
+    {
+        if (threads < 1) threads = 1;
+        if (threads > kMaxThreads) threads = kMaxThreads;
+        if (n < ((size_t)1 << 20) || threads == 1) { std::memcpy(d, s, n); return; }
+        std::lock_guard<std::mutex> call(call_mu_);                                 // one job at a time (pipes of several devices share the pool)
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while ((int)workers_.size() < threads - 1) {
+                const int idx = (int)workers_.size();
+                workers_.emplace_back([this, idx] { run(idx); });
+                workers_.back().detach();
+            }
+            d_ = (char*)d; s_ = (const char*)s; n_ = n; parts_ = threads; pending_ = threads - 1;
+            ++gen_;
+        }
+        cv_job_.notify_all();
+        slice(threads - 1);                                                         // the caller takes the last part
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    static const int kMaxThreads = 16;
+    void slice(int i)
+    {
+        const size_t a = (n_ * (size_t)i / parts_) & ~(size_t)63, b = i == parts_ - 1 ? n_ : ((n_ * (size_t)(i + 1) / parts_) & ~(size_t)63);
+        if (b > a) std::memcpy(d_ + a, s_ + a, b - a);
+    }
+    void run(int idx)
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_job_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (idx >= parts_ - 1) continue;                                    // this job uses fewer threads
+            }
+            slice(idx);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) cv_done_.notify_one();
+        }
+    }
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_job_, cv_done_;
+    std::vector<std::thread> workers_;
+    char* d_ = nullptr; const char* s_ = nullptr; size_t n_ = 0;
+    int parts_ = 1, pending_ = 0;
+    unsigned long gen_ = 0;
+};
+
+bool is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
 
 void drain(HostPipe& P)
 {
@@ -97,6 +169,7 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
         for (int i = 0; i < kMaxBands; ++i) {
             GF_CU(cudaEventCreateWithFlags(&P.ev_up[i], cudaEventDisableTiming));
             GF_CU(cudaEventCreateWithFlags(&P.ev_k[i], cudaEventDisableTiming));
+            GF_CU(cudaEventCreateWithFlags(&P.ev_down[i], cudaEventDisableTiming));
         }
         P.init = true;
     }
@@ -110,15 +183,32 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
         P.cap = n;
     }
     float *dI = P.dev, *dP = P.dev + P.cap, *dQ = P.dev + 2 * P.cap;
+    // pageable buffers are staged through pinned planes by the copy pool; pinned / registered ones are copied directly
+    // copy threads: half of the machine's cores, 2..8.  4K frame on the 16-core GPU box (profiles/r2_e2e_pageable_staged.jsonl):
+    // 4 threads 3.9-4.5 ms, 8: 3.0-3.5, 12: 2.85-3.3, 16: 2.8; the driver's own pageable copies: 6.9-8.0 ms
+    static const int dflt_threads = [] { const int c = (int)std::thread::hardware_concurrency() / 2; return c < 2 ? 2 : (c > 8 ? 8 : c); }();
+    const int copy_threads = GF_KNOB("GF_HOST_COPY_THREADS", dflt_threads);
+    const bool staged = GF_KNOB("GF_HOST_STAGED", 1) && copy_threads > 0 && (is_pageable(guide) || is_pageable(src) || is_pageable(dst));
+    if (staged && n > P.pin_cap) {
+        if (P.pin) GF_CU(cudaFreeHost(P.pin));
+        P.pin = nullptr;
+        P.pin_cap = 0;
+        cudaError_t e = cudaHostAlloc((void**)&P.pin, 3 * n * sizeof(float), cudaHostAllocDefault);
+        if (e != cudaSuccess) { P.pin = nullptr; return fail(GF_ERR_NOMEM, "pinned staging planes (%zu bytes): %s", 3 * n * sizeof(float), cudaGetErrorString(e)); }
+        P.pin_cap = n;
+    }
+    float *hI = staged ? P.pin : nullptr, *hP = staged ? P.pin + P.pin_cap : nullptr, *hQ = staged ? P.pin + 2 * P.pin_cap : nullptr;
     int nb = height / (4 * r + 64);
     // measured on B200 / PCIe Gen5 (4K frame; bench_tools/e2e_check.py, pcie_pipe.py): 1 band 1.89 ms, 2: 1.67, 4: 1.61,
     // 8: 1.75, 16: 1.65 -- chunked copies lose duplex efficiency, so few large bands win (ideal duplex: 1.27 ms)
     nb = nb < 1 ? 1 : (nb > 4 ? 4 : nb);
-    nb = GF_KNOB("GF_HOST_BANDS", nb); nb = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
+    // staged copies are bound by the CPU copies, which only overlap the DMA of OTHER bands: more, equal bands
+    if (staged) nb = height / (4 * r + 64) < 1 ? 1 : (height / (4 * r + 64) > 12 ? 12 : height / (4 * r + 64));
+    nb = GF_KNOB(staged ? "GF_HOST_STAGED_BANDS" : "GF_HOST_BANDS", nb); nb = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
     // band b is taper % as tall as band b-1: what stays exposed at the end is the kernel and the download of the LAST band.
     // Measured (4K frame, profiles/r2_e2e_bands_taper.jsonl): 4 uniform bands 1.60 ms, taper 80 %: 1.57, 65 %: 1.54,
     // 50-55 %: 1.50, 35 %: 1.54, 25 %: 1.62 (1 band, no overlap: 1.87; upload alone ~1.2).
-    int taper = GF_KNOB("GF_HOST_TAPER_PCT", 50);
+    int taper = staged ? 100 : GF_KNOB("GF_HOST_TAPER_PCT", 50);
     taper = taper < 20 ? 20 : (taper > 100 ? 100 : taper);
     int cut[kMaxBands + 1];
     {
@@ -133,6 +223,18 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
         }
     }
     int up_to = 0;
+    int out_done = 0;               // staged: bands [0, out_done) have been copied from the pinned dst plane to the caller's
+    auto copy_out = [&](int upto_band, bool wait) -> cudaError_t {
+        for (; out_done < upto_band; ++out_done) {
+            const int a = cut[out_done], e = cut[out_done + 1];
+            if (e <= a) continue;
+            if (!wait && cudaEventQuery(P.ev_down[out_done]) != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
+            const cudaError_t rc = cudaEventSynchronize(P.ev_down[out_done]);
+            if (rc != cudaSuccess) return rc;
+            CopyPool::get().copy(dst + (size_t)a * width, hQ + (size_t)a * width, (size_t)(e - a) * width * sizeof(float), copy_threads);
+        }
+        return cudaSuccess;
+    };
     for (int b = 0; b < nb; ++b) {
         const int y0 = cut[b], y1 = cut[b + 1];
         if (y1 <= y0) continue;
@@ -140,8 +242,15 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
         if (need > height || b == nb - 1) need = height;
         if (need > up_to) {
             const size_t off = (size_t)up_to * width, cnt = (size_t)(need - up_to) * width * sizeof(float);
-            GF_CU_DRAIN(cudaMemcpyAsync(dI + off, guide + off, cnt, cudaMemcpyHostToDevice, P.up));
-            GF_CU_DRAIN(cudaMemcpyAsync(dP + off, src + off, cnt, cudaMemcpyHostToDevice, P.up));
+            if (staged) {
+                CopyPool::get().copy(hI + off, guide + off, cnt, copy_threads);
+                GF_CU_DRAIN(cudaMemcpyAsync(dI + off, hI + off, cnt, cudaMemcpyHostToDevice, P.up));
+                CopyPool::get().copy(hP + off, src + off, cnt, copy_threads);
+                GF_CU_DRAIN(cudaMemcpyAsync(dP + off, hP + off, cnt, cudaMemcpyHostToDevice, P.up));
+            } else {
+                GF_CU_DRAIN(cudaMemcpyAsync(dI + off, guide + off, cnt, cudaMemcpyHostToDevice, P.up));
+                GF_CU_DRAIN(cudaMemcpyAsync(dP + off, src + off, cnt, cudaMemcpyHostToDevice, P.up));
+            }
             up_to = need;
         }
         GF_CU_DRAIN(cudaEventRecord(P.ev_up[b], P.up));
@@ -152,9 +261,14 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
         if (rc) { drain(P); return rc; }
         GF_CU_DRAIN(cudaEventRecord(P.ev_k[b], P.comp));
         GF_CU_DRAIN(cudaStreamWaitEvent(P.down, P.ev_k[b], 0));
-        GF_CU_DRAIN(cudaMemcpyAsync(dst + (size_t)y0 * width, dQ + (size_t)y0 * width, (size_t)(y1 - y0) * width * sizeof(float),
+        GF_CU_DRAIN(cudaMemcpyAsync((staged ? hQ : dst) + (size_t)y0 * width, dQ + (size_t)y0 * width, (size_t)(y1 - y0) * width * sizeof(float),
                               cudaMemcpyDeviceToHost, P.down));
+        if (staged) {
+            GF_CU_DRAIN(cudaEventRecord(P.ev_down[b], P.down));
+            GF_CU_DRAIN(copy_out(b, false));        // bands whose download has already landed, without waiting
+        }
     }
+    if (staged) GF_CU_DRAIN(copy_out(nb, true));
     GF_CU(cudaStreamSynchronize(P.down));
     GF_CU(cudaStreamSynchronize(P.comp));
     return GF_OK;

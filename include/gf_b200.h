@@ -178,8 +178,9 @@ int gf_linear_transform(const float* src, float* dst, const float* a, const floa
 /* ---- host-buffer entry (what a caller with cv::Mat data uses; the `e2e` number) ------------ */
 
 /* Gray filter on HOST buffers (tightly packed rows): H2D of guide and src, the fused kernel,
-   D2H of dst, pipelined in row bands over internal pinned staging and streams; returns when
-   dst is complete.  Replaces the cudaMemcpy2D + hGuidedFilter + cudaMemcpy2D sequence of
+   D2H of dst, pipelined in row bands over internal streams; returns when dst is complete.
+   Pinned (gf_host_alloc) or registered (gf_host_register) buffers are copied by the DMA engines
+   directly; pageable buffers are staged through pinned planes by a few copy threads of the library.  Replaces the cudaMemcpy2D + hGuidedFilter + cudaMemcpy2D sequence of
    main.cpp:229-279. */
 int gf_guided_gray_host(const float* guide, const float* src, float* dst, int width, int height,
                         int r, float eps, int border);
