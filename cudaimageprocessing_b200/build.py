@@ -76,15 +76,30 @@ def build_variant(name: str, defines: list[str]) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Builds the library if it is missing or older than its sources.  Safe when several processes import the package
+    at once (one rank per GPU under torchrun): an exclusive file lock serialises the check and the build, the link goes
+    to a temporary name and is renamed into place, and whoever gets the lock second finds a fresh library."""
+    import fcntl
     if not force and not _stale():
         return LIB
-    rc, text = _compile_and_link(LIB, [])
-    if verbose or rc != 0:
-        sys.stderr.write(text)
-    if rc != 0:
-        raise RuntimeError("nvcc failed building libgf_b200.so")
-    with open(os.path.join(PKG, "build_ptxas.log"), "w") as f:
-        f.write(text)
+    with open(os.path.join(PKG, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB
+            tmp = LIB + f".tmp{os.getpid()}"
+            rc, text = _compile_and_link(tmp, [])
+            if verbose or rc != 0:
+                sys.stderr.write(text)
+            if rc != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libgf_b200.so")
+            os.replace(tmp, LIB)
+            with open(os.path.join(PKG, "build_ptxas.log"), "w") as f:
+                f.write(text)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

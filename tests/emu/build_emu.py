@@ -14,8 +14,21 @@ def build_emu(force: bool = False) -> str:
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + \
            [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp")] + \
            [os.path.join(ROOT, "include", "gf_b200.h")]
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+    fresh = lambda: os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps)
+    if not force and fresh():
         return LIB
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:     # several test processes may get here at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return LIB
+            return _build(deps)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build(deps) -> str:
     import tempfile
     from concurrent.futures import ThreadPoolExecutor
     flags = ["-O1", "-std=c++17", "-fopenmp", "-fPIC", "-DGF_CPU_EMU", "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -29,7 +42,9 @@ def build_emu(force: bool = False) -> str:
             return obj
         with ThreadPoolExecutor(max_workers=5) as ex:          # one translation unit per kernel family, in parallel
             objs = list(ex.map(one, units))
-        subprocess.check_call(["/usr/bin/g++", "-shared", "-fopenmp", "-o", LIB] + objs)
+        tmp_lib = LIB + f".tmp{os.getpid()}"
+        subprocess.check_call(["/usr/bin/g++", "-shared", "-fopenmp", "-o", tmp_lib] + objs)
+        os.replace(tmp_lib, LIB)
     return LIB
 
 
