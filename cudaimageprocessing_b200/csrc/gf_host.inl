@@ -3,11 +3,10 @@
 // gf_guided_gray_host is the end-to-end call: it uploads guide and src, filters, and downloads
 // dst, pipelined in row bands over three streams so that H2D of band b+1, the kernel of band b
 // and D2H of band b-1 overlap (PCIe is full duplex; the kernel is ~1% of the copy time).
-#include <condition_variable>
-#include <cstring>
 #include <mutex>
 #include <thread>
-#include <vector>
+
+#include "gf_copy_pool.h"
 
 #ifdef GF_CPU_EMU
 extern "C" {
@@ -54,61 +53,6 @@ HostPipe g_pipes[kMaxDevices];
 // staged copy inside the driver (4K frame: 6.9 ms against 1.5 ms from pinned memory).  The host call stages such
 // buffers itself: a few threads copy each row band between the caller's memory and pinned planes while the DMA engine
 // moves the previous band (profiles/r2_e2e_pageable_staged.jsonl).
-class CopyPool {
-public:
-    static CopyPool& get() { static CopyPool* p = new CopyPool(); return *p; }     // never destroyed: workers outlive main()
-    void copy(void* d, const void* s, size_t n, int threads)
-    {
-        if (threads < 1) threads = 1;
-        if (threads > kMaxThreads) threads = kMaxThreads;
-        if (n < ((size_t)1 << 20) || threads == 1) { std::memcpy(d, s, n); return; }
-        std::lock_guard<std::mutex> call(call_mu_);                                 // one job at a time (pipes of several devices share the pool)
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            while ((int)workers_.size() < threads - 1) {
-                const int idx = (int)workers_.size();
-                workers_.emplace_back([this, idx] { run(idx); });
-                workers_.back().detach();
-            }
-            d_ = (char*)d; s_ = (const char*)s; n_ = n; parts_ = threads; pending_ = threads - 1;
-            ++gen_;
-        }
-        cv_job_.notify_all();
-        slice(threads - 1);                                                         // the caller takes the last part
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_done_.wait(lk, [this] { return pending_ == 0; });
-    }
-
-private:
-    static const int kMaxThreads = 16;
-    void slice(int i)
-    {
-        const size_t a = (n_ * (size_t)i / parts_) & ~(size_t)63, b = i == parts_ - 1 ? n_ : ((n_ * (size_t)(i + 1) / parts_) & ~(size_t)63);
-        if (b > a) std::memcpy(d_ + a, s_ + a, b - a);
-    }
-    void run(int idx)
-    {
-        unsigned long seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_job_.wait(lk, [&] { return gen_ != seen; });
-                seen = gen_;
-                if (idx >= parts_ - 1) continue;                                    // this job uses fewer threads
-            }
-            slice(idx);
-            std::lock_guard<std::mutex> lk(mu_);
-            if (--pending_ == 0) cv_done_.notify_one();
-        }
-    }
-    std::mutex mu_, call_mu_;
-    std::condition_variable cv_job_, cv_done_;
-    std::vector<std::thread> workers_;
-    char* d_ = nullptr; const char* s_ = nullptr; size_t n_ = 0;
-    int parts_ = 1, pending_ = 0;
-    unsigned long gen_ = 0;
-};
-
 bool is_pageable(const void* p)
 {
     cudaPointerAttributes a;
@@ -231,7 +175,7 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
             if (!wait && cudaEventQuery(P.ev_down[out_done]) != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
             const cudaError_t rc = cudaEventSynchronize(P.ev_down[out_done]);
             if (rc != cudaSuccess) return rc;
-            CopyPool::get().copy(dst + (size_t)a * width, hQ + (size_t)a * width, (size_t)(e - a) * width * sizeof(float), copy_threads);
+            GfCopyPool::get().copy(dst + (size_t)a * width, hQ + (size_t)a * width, (size_t)(e - a) * width * sizeof(float), copy_threads);
         }
         return cudaSuccess;
     };
@@ -243,9 +187,9 @@ int gf_guided_gray_host(const float* guide, const float* src, float* dst, int wi
         if (need > up_to) {
             const size_t off = (size_t)up_to * width, cnt = (size_t)(need - up_to) * width * sizeof(float);
             if (staged) {
-                CopyPool::get().copy(hI + off, guide + off, cnt, copy_threads);
+                GfCopyPool::get().copy(hI + off, guide + off, cnt, copy_threads);
                 GF_CU_DRAIN(cudaMemcpyAsync(dI + off, hI + off, cnt, cudaMemcpyHostToDevice, P.up));
-                CopyPool::get().copy(hP + off, src + off, cnt, copy_threads);
+                GfCopyPool::get().copy(hP + off, src + off, cnt, copy_threads);
                 GF_CU_DRAIN(cudaMemcpyAsync(dP + off, hP + off, cnt, cudaMemcpyHostToDevice, P.up));
             } else {
                 GF_CU_DRAIN(cudaMemcpyAsync(dI + off, guide + off, cnt, cudaMemcpyHostToDevice, P.up));
