@@ -1,6 +1,10 @@
+"""Developer tool (ONE GPU): the equal-cost "tape" split (GF_TAPE=1) against uniform bands for the r = 16 gray kernel on the
+strip geometry of BASELINE configs[4] (32768 x 4096 per GPU at 8 GPUs), the whole 32768^2 image, and 4K / 8K frames.
+Result (B200): the tape does not help gray strips (0.928 vs 0.923 ms) and costs 7 % on the whole image."""
 import ctypes, json, os, sys
 import torch
-sys.path.insert(0, "/root/repo")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import cudaimageprocessing_b200 as pkg
 api = pkg.api()
 s = torch.cuda.current_stream(); sp = ctypes.c_void_p(s.cuda_stream)
